@@ -1,0 +1,106 @@
+/*
+ * crscene_io.c — save/load the flat scene description of include/crscene.h.
+ *
+ * File layout: [u32 magic][u32 version][u64 total bytes][struct crs_scene with NULL pointers]
+ * followed by the 14 arrays in the order they are declared in struct crs_scene, each starting on a
+ * 16-byte boundary.  No reference counterpart: c-ray never serialises its scene (the cluster mode
+ * re-sends the JSON, reference src/utils/protocol/server.c:296-323).
+ */
+#include "../../include/crscene.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct section { const void *ptr; size_t bytes; };
+
+static size_t align16(size_t x) { return (x + 15u) & ~(size_t)15u; }
+
+static void sections_of(const struct crs_scene *s, struct section sec[14]) {
+	sec[0]  = (struct section){ s->instances,    (size_t)s->instance_count   * sizeof(struct crs_instance) };
+	sec[1]  = (struct section){ s->spheres,      (size_t)s->sphere_count     * sizeof(struct crs_sphere) };
+	sec[2]  = (struct section){ s->meshes,       (size_t)s->mesh_count       * sizeof(struct crs_mesh) };
+	sec[3]  = (struct section){ s->materials,    (size_t)s->material_count   * sizeof(struct crs_material) };
+	sec[4]  = (struct section){ s->nodes,        (size_t)s->node_count       * sizeof(struct crs_node) };
+	sec[5]  = (struct section){ s->textures,     (size_t)s->texture_count    * sizeof(struct crs_texture) };
+	sec[6]  = (struct section){ s->bvhs,         (size_t)s->bvh_count        * sizeof(struct crs_bvh) };
+	sec[7]  = (struct section){ s->bvh_nodes,    (size_t)s->bvh_node_count   * sizeof(struct crs_bvh_node) };
+	sec[8]  = (struct section){ s->prim_indices, (size_t)s->prim_index_count * sizeof(int32_t) };
+	sec[9]  = (struct section){ s->polys,        (size_t)s->poly_count       * sizeof(struct crs_poly) };
+	sec[10] = (struct section){ s->vertices,     (size_t)s->vertex_count     * 3 * sizeof(float) };
+	sec[11] = (struct section){ s->normals,      (size_t)s->normal_count     * 3 * sizeof(float) };
+	sec[12] = (struct section){ s->texcoords,    (size_t)s->texcoord_count   * 2 * sizeof(float) };
+	sec[13] = (struct section){ s->texdata,      (size_t)s->texdata_bytes };
+}
+
+static size_t header_bytes(void) { return align16(16 + sizeof(struct crs_scene)); }
+
+int crscene_save(const struct crs_scene *s, const char *path) {
+	struct section sec[14];
+	sections_of(s, sec);
+	size_t total = header_bytes();
+	for (int i = 0; i < 14; ++i) total += align16(sec[i].bytes);
+
+	FILE *f = fopen(path, "wb");
+	if (!f) return -1;
+	uint32_t magic = CRS_MAGIC, version = CRS_VERSION;
+	uint64_t total64 = total;
+	struct crs_scene copy = *s;
+	copy.instances = NULL; copy.spheres = NULL; copy.meshes = NULL; copy.materials = NULL;
+	copy.nodes = NULL; copy.textures = NULL; copy.bvhs = NULL; copy.bvh_nodes = NULL;
+	copy.prim_indices = NULL; copy.polys = NULL; copy.vertices = NULL; copy.normals = NULL;
+	copy.texcoords = NULL; copy.texdata = NULL; copy.owner = NULL;
+	static const char zeros[16] = {0};
+	int ok = 1;
+	ok &= fwrite(&magic, 4, 1, f) == 1;
+	ok &= fwrite(&version, 4, 1, f) == 1;
+	ok &= fwrite(&total64, 8, 1, f) == 1;
+	ok &= fwrite(&copy, sizeof(copy), 1, f) == 1;
+	size_t pad = header_bytes() - (16 + sizeof(copy));
+	if (pad) ok &= fwrite(zeros, 1, pad, f) == pad;
+	for (int i = 0; i < 14 && ok; ++i) {
+		if (sec[i].bytes) ok &= fwrite(sec[i].ptr, 1, sec[i].bytes, f) == sec[i].bytes;
+		pad = align16(sec[i].bytes) - sec[i].bytes;
+		if (pad) ok &= fwrite(zeros, 1, pad, f) == pad;
+	}
+	if (fclose(f) != 0) ok = 0;
+	return ok ? 0 : -2;
+}
+
+int crscene_load(struct crs_scene *out, const char *path) {
+	memset(out, 0, sizeof(*out));
+	FILE *f = fopen(path, "rb");
+	if (!f) return -1;
+	if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return -2; }
+	long size = ftell(f);
+	if (size < (long)header_bytes()) { fclose(f); return -3; }
+	rewind(f);
+	uint8_t *buf = NULL;
+	if (posix_memalign((void **)&buf, 64, (size_t)size) != 0) { fclose(f); return -4; }
+	if (fread(buf, 1, (size_t)size, f) != (size_t)size) { fclose(f); free(buf); return -2; }
+	fclose(f);
+	uint32_t magic, version;
+	uint64_t total;
+	memcpy(&magic, buf, 4); memcpy(&version, buf + 4, 4); memcpy(&total, buf + 8, 8);
+	if (magic != CRS_MAGIC || version != CRS_VERSION || total != (uint64_t)size) { free(buf); return -5; }
+	memcpy(out, buf + 16, sizeof(*out));
+	struct section sec[14];
+	sections_of(out, sec); /* sizes only; pointers are NULL in the file */
+	size_t off = header_bytes();
+	void *ptrs[14];
+	for (int i = 0; i < 14; ++i) {
+		if (off + sec[i].bytes > (size_t)size) { free(buf); memset(out, 0, sizeof(*out)); return -6; }
+		ptrs[i] = sec[i].bytes ? buf + off : NULL;
+		off += align16(sec[i].bytes);
+	}
+	out->instances = ptrs[0]; out->spheres = ptrs[1]; out->meshes = ptrs[2]; out->materials = ptrs[3];
+	out->nodes = ptrs[4]; out->textures = ptrs[5]; out->bvhs = ptrs[6]; out->bvh_nodes = ptrs[7];
+	out->prim_indices = ptrs[8]; out->polys = ptrs[9]; out->vertices = ptrs[10]; out->normals = ptrs[11];
+	out->texcoords = ptrs[12]; out->texdata = ptrs[13];
+	out->owner = buf;
+	return 0;
+}
+
+void crscene_free(struct crs_scene *s) {
+	if (s && s->owner) free(s->owner);
+	if (s) memset(s, 0, sizeof(*s));
+}
