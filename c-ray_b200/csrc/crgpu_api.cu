@@ -1,0 +1,602 @@
+/*
+ * crgpu_api.cu — C ABI of libcrgpu.so (include/crgpu.h): scene upload, the per-tile wavefront driver,
+ * framebuffer access.  Host code here only lays data out in HBM and launches kernels; all arithmetic
+ * of the hot path is in the kernels (crgpu_kernels.cuh).  No CPU fallback exists.
+ */
+#include "../../include/crgpu.h"
+#include "crgpu_wave.cuh"
+#include "crgpu_scene.cuh"
+
+#define CRG_NODE_DEPTH 3
+#define CRG_ADD_STACK 4
+#define CRG_HITKAT_BYTES 160
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <vector>
+#include <queue>
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+	va_list vl;
+	va_start(vl, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, vl);
+	va_end(vl);
+	return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(CRGPU_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" const char *crgpu_last_error(void) { return g_err; }
+
+extern "C" int crgpu_device_count(int *n) {
+	if (!n) return fail(CRGPU_ERR_BAD_ARGUMENT, "n is NULL");
+	int c = 0;
+	cudaError_t e = cudaGetDeviceCount(&c);
+	if (e != cudaSuccess || c < 1) { *n = 0; return fail(CRGPU_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
+	*n = c;
+	return CRGPU_OK;
+}
+
+struct crgpu_scene {
+	int device;
+	int sm_count;
+	cudaStream_t stream;
+	DevScene dev;
+	DevScene *dev_copy;        /* the same descriptor in HBM, for kernels that call noinline device functions */
+	std::vector<void *> allocs;
+	float *fb;                 /* W*H*3 fp32, row H-1-y */
+	uint8_t *fb8;              /* lazily allocated sRGB8 staging */
+	size_t fb_floats;
+	uint64_t max_paths;
+	uint64_t cap_paths;        /* capacity of the wavefront buffers */
+	WaveBuffers wb;
+	cudaEvent_t ev[4];
+};
+
+template <class T>
+static int upload(crgpu_scene *s, const std::vector<T> &v, const T **out) {
+	void *p = nullptr;
+	size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+	CU(cudaMalloc(&p, bytes));
+	s->allocs.push_back(p);
+	if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+	*out = static_cast<const T *>(p);
+	return CRGPU_OK;
+}
+
+/* ---- node graph checks -------------------------------------------------------------------------------------- */
+static bool node_ok(const crs_scene *f, int idx) { return idx >= 0 && (uint32_t)idx < f->node_count; }
+
+/* nesting depth of color->value->color recursion below a color/value node (checker A/B are tail calls) */
+static int value_depth(const crs_scene *f, int idx, int guard);
+static int color_depth(const crs_scene *f, int idx, int guard) {
+	if (!node_ok(f, idx) || guard > 64) return 1000;
+	const crs_node &n = f->nodes[idx];
+	switch (n.kind) {
+	case CRS_COLOR_CONSTANT: case CRS_COLOR_IMAGE: case CRS_COLOR_GRADIENT: return 0;
+	case CRS_COLOR_CHECKER: {
+		int a = color_depth(f, n.in[0], guard + 1), b = color_depth(f, n.in[1], guard + 1);
+		int v = 1 + value_depth(f, n.in[2], guard + 1);
+		int m = a > b ? a : b;
+		return m > v ? m : v;
+	}
+	case CRS_COLOR_BLACKBODY: return 1 + value_depth(f, n.in[0], guard + 1);
+	default: return 1000;
+	}
+}
+static int value_depth(const crs_scene *f, int idx, int guard) {
+	if (!node_ok(f, idx) || guard > 64) return 1000;
+	const crs_node &n = f->nodes[idx];
+	switch (n.kind) {
+	case CRS_VALUE_CONSTANT: return 0;
+	case CRS_VALUE_GRAYSCALE: case CRS_VALUE_ALPHA: return color_depth(f, n.in[0], guard + 1);
+	default: return 1000;
+	}
+}
+static bool color_reads_uv(const crs_scene *f, int idx);
+static bool value_reads_uv(const crs_scene *f, int idx) {
+	if (!node_ok(f, idx)) return false;
+	const crs_node &n = f->nodes[idx];
+	return (n.kind == CRS_VALUE_GRAYSCALE || n.kind == CRS_VALUE_ALPHA) && color_reads_uv(f, n.in[0]);
+}
+static bool color_reads_uv(const crs_scene *f, int idx) {
+	if (!node_ok(f, idx)) return false;
+	const crs_node &n = f->nodes[idx];
+	switch (n.kind) {
+	case CRS_COLOR_IMAGE: case CRS_COLOR_CHECKER: return true;
+	case CRS_COLOR_BLACKBODY: return value_reads_uv(f, n.in[0]);
+	default: return false;
+	}
+}
+/* validates a bsdf tree; *add_depth = nesting of ADD nodes; *uv = some node reads uv */
+static int check_bsdf(const crs_scene *f, int idx, int add_level, int guard, bool *uv) {
+	if (!node_ok(f, idx) || guard > 64) return fail(CRGPU_ERR_UNSUPPORTED, "bsdf node index %d out of range or graph too deep", idx);
+	const crs_node &n = f->nodes[idx];
+	auto col = [&](int c) -> int {
+		if (color_depth(f, c, 0) > CRG_NODE_DEPTH) return fail(CRGPU_ERR_UNSUPPORTED, "color node %d nests deeper than %d", c, CRG_NODE_DEPTH);
+		if (color_reads_uv(f, c)) *uv = true;
+		return 0;
+	};
+	auto val = [&](int v) -> int {
+		if (value_depth(f, v, 0) > CRG_NODE_DEPTH) return fail(CRGPU_ERR_UNSUPPORTED, "value node %d nests deeper than %d", v, CRG_NODE_DEPTH);
+		if (value_reads_uv(f, v)) *uv = true;
+		return 0;
+	};
+	int rc;
+	switch (n.kind) {
+	case CRS_BSDF_DIFFUSE: case CRS_BSDF_TRANSPARENT: case CRS_BSDF_ISOTROPIC: return col(n.in[0]);
+	case CRS_BSDF_METAL: case CRS_BSDF_EMISSIVE: if ((rc = col(n.in[0]))) return rc; return val(n.in[1]);
+	case CRS_BSDF_GLASS: case CRS_BSDF_BACKGROUND:
+		if ((rc = col(n.in[0]))) return rc; if ((rc = val(n.in[1]))) return rc; return val(n.in[2]);
+	case CRS_BSDF_PLASTIC:
+		if ((rc = col(n.in[0]))) return rc; if ((rc = col(n.in[1]))) return rc;
+		return check_bsdf(f, n.in[2], add_level, guard + 1, uv);
+	case CRS_BSDF_MIX:
+		if ((rc = val(n.in[2]))) return rc;
+		if ((rc = check_bsdf(f, n.in[0], add_level, guard + 1, uv))) return rc;
+		return check_bsdf(f, n.in[1], add_level, guard + 1, uv);
+	case CRS_BSDF_ADD:
+		if (2 * (add_level + 1) > CRG_ADD_STACK) return fail(CRGPU_ERR_UNSUPPORTED, "ADD nodes nest deeper than %d", CRG_ADD_STACK / 2);
+		if ((rc = check_bsdf(f, n.in[0], add_level + 1, guard + 1, uv))) return rc;
+		return check_bsdf(f, n.in[1], add_level + 1, guard + 1, uv);
+	default: return fail(CRGPU_ERR_UNSUPPORTED, "node %d has kind %d where a bsdf is expected", idx, n.kind);
+	}
+}
+
+/* ---- BVH re-layout: reference nodes (bvh.c:37-42) -> BFS-ordered PairNodes ---------------------------------------- */
+static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNode> &pairs, DevBvh &out, uint32_t slot_offset) {
+	memset(&out, 0, sizeof out);
+	out.pair_offset = (uint32_t)pairs.size();
+	out.node_count = b.node_count;
+	out.slot_offset = slot_offset;
+	if (b.node_count == 0) return CRGPU_OK;
+	const crs_bvh_node *nodes = f->bvh_nodes + b.node_offset;
+	if (b.node_count == 1) {
+		memcpy(out.root_bounds, nodes[0].bounds, sizeof out.root_bounds);
+		out.root_first = nodes[0].first_child_or_prim;
+		out.root_count = nodes[0].prim_count_leaf & CRS_BVH_COUNT_MASK;
+		return CRGPU_OK;
+	}
+	/* BFS over internal nodes; pair index = BFS rank */
+	std::vector<uint32_t> order;            /* reference node index of each internal node, BFS order */
+	std::vector<uint32_t> rank(b.node_count, 0xffffffffu);
+	order.push_back(0);
+	rank[0] = 0;
+	for (size_t head = 0; head < order.size(); ++head) {
+		const crs_bvh_node &n = nodes[order[head]];
+		if (n.prim_count_leaf & CRS_BVH_LEAF_BIT) return fail(CRGPU_ERR_BAD_ARGUMENT, "BVH root/internal node is a leaf");
+		const uint32_t fc = n.first_child_or_prim;
+		if (fc + 1 >= b.node_count) return fail(CRGPU_ERR_BAD_ARGUMENT, "BVH child index out of range");
+		for (uint32_t k = 0; k < 2; ++k) {
+			const crs_bvh_node &c = nodes[fc + k];
+			if (!(c.prim_count_leaf & CRS_BVH_LEAF_BIT)) {
+				if (rank[fc + k] != 0xffffffffu) return fail(CRGPU_ERR_BAD_ARGUMENT, "BVH is not a tree");
+				rank[fc + k] = (uint32_t)order.size();
+				order.push_back(fc + k);
+			}
+		}
+	}
+	for (size_t r = 0; r < order.size(); ++r) {
+		const crs_bvh_node &n = nodes[order[r]];
+		const uint32_t fc = n.first_child_or_prim;
+		PairNode p;
+		memset(&p, 0, sizeof p);
+		const crs_bvh_node &l = nodes[fc], &rr = nodes[fc + 1];
+		memcpy(p.lb, l.bounds, sizeof p.lb);
+		memcpy(p.rb, rr.bounds, sizeof p.rb);
+		if (l.prim_count_leaf & CRS_BVH_LEAF_BIT) { p.lref = l.first_child_or_prim; p.lmeta = CRG_LEAF_BIT | (l.prim_count_leaf & CRS_BVH_COUNT_MASK); }
+		else { p.lref = rank[fc]; p.lmeta = 0; }
+		if (rr.prim_count_leaf & CRS_BVH_LEAF_BIT) { p.rref = rr.first_child_or_prim; p.rmeta = CRG_LEAF_BIT | (rr.prim_count_leaf & CRS_BVH_COUNT_MASK); }
+		else { p.rref = rank[fc + 1]; p.rmeta = 0; }
+		pairs.push_back(p);
+	}
+	return CRGPU_OK;
+}
+
+static inline void f3(float *dst, const float *src, size_t idx) { dst[0] = src[3 * idx]; dst[1] = src[3 * idx + 1]; dst[2] = src[3 * idx + 2]; }
+
+static int alloc_wave(crgpu_scene *s, uint64_t paths) {
+	if (paths <= s->cap_paths) return CRGPU_OK;
+	WaveBuffers &w = s->wb;
+	void **ptrs[] = { (void **)&w.stA[0], (void **)&w.stA[1], (void **)&w.stB[0], (void **)&w.stB[1], (void **)&w.stC[0],
+					  (void **)&w.stC[1], (void **)&w.hit, (void **)&w.hitInst, (void **)&w.L };
+	for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+	s->cap_paths = 0;
+	const size_t n = (size_t)paths;
+	CU(cudaMalloc((void **)&w.stA[0], n * 16)); CU(cudaMalloc((void **)&w.stA[1], n * 16));
+	CU(cudaMalloc((void **)&w.stB[0], n * 16)); CU(cudaMalloc((void **)&w.stB[1], n * 16));
+	CU(cudaMalloc((void **)&w.stC[0], n * 16)); CU(cudaMalloc((void **)&w.stC[1], n * 16));
+	CU(cudaMalloc((void **)&w.hit, n * 16)); CU(cudaMalloc((void **)&w.hitInst, n * 4));
+	CU(cudaMalloc((void **)&w.L, n * 16));
+	s->cap_paths = paths;
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_scene_destroy(crgpu_scene *s) {
+	if (!s) return CRGPU_OK;
+	cudaSetDevice(s->device);
+	if (s->stream) cudaStreamSynchronize(s->stream);
+	for (void *p : s->allocs) cudaFree(p);
+	WaveBuffers &w = s->wb;
+	void *ptrs[] = { w.stA[0], w.stA[1], w.stB[0], w.stB[1], w.stC[0], w.stC[1], w.hit, w.hitInst, w.L, w.counts, w.stats, s->fb, s->fb8 };
+	for (void *p : ptrs) if (p) cudaFree(p);
+	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
+	if (s->stream) cudaStreamDestroy(s->stream);
+	delete s;
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_scene **out) {
+	if (!f || !out) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
+	*out = nullptr;
+	int ndev = 0;
+	int rc = crgpu_device_count(&ndev);
+	if (rc) return rc;
+	if (device < 0 || device >= ndev) return fail(CRGPU_ERR_BAD_ARGUMENT, "device %d out of range (have %d)", device, ndev);
+	if (f->prefs.image_width == 0 || f->prefs.image_height == 0 || f->prefs.sample_count == 0)
+		return fail(CRGPU_ERR_BAD_ARGUMENT, "empty image or zero samples");
+	if (!node_ok(f, f->background) || f->nodes[f->background].kind != CRS_BSDF_BACKGROUND)
+		return fail(CRGPU_ERR_UNSUPPORTED, "scene background must be a background node");
+	if (f->top_bvh >= f->bvh_count) return fail(CRGPU_ERR_BAD_ARGUMENT, "top_bvh out of range");
+	CU(cudaSetDevice(device));
+
+	crgpu_scene *s = new crgpu_scene();
+	memset(&s->dev, 0, sizeof s->dev);
+	memset(&s->wb, 0, sizeof s->wb);
+	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->cap_paths = 0;
+	s->max_paths = 8ull << 20;
+	for (auto &e : s->ev) e = nullptr;
+#define FAIL_IF(x) do { int rc_ = (x); if (rc_) { crgpu_scene_destroy(s); return rc_; } } while (0)
+#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(CRGPU_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); crgpu_scene_destroy(s); return rc_; } } while (0)
+	cudaDeviceProp prop;
+	CUS(cudaGetDeviceProperties(&prop, device));
+	s->sm_count = prop.multiProcessorCount;
+	CUS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	for (auto &e : s->ev) CUS(cudaEventCreate(&e));
+
+	/* materials + graph validation */
+	std::vector<DevMaterial> mats(f->material_count);
+	{
+		bool uv = false;
+		FAIL_IF(check_bsdf(f, f->background, 0, 0, &uv));
+	}
+	for (uint32_t i = 0; i < f->material_count; ++i) {
+		const crs_material &m = f->materials[i];
+		bool uv = false;
+		FAIL_IF(check_bsdf(f, m.bsdf, 0, 0, &uv));
+		DevMaterial d;
+		memset(&d, 0, sizeof d);
+		d.emission[0] = m.emission[0]; d.emission[1] = m.emission[1]; d.emission[2] = m.emission[2];
+		d.IOR = m.IOR; d.bsdf = m.bsdf;
+		/* x + w*0 == x bit-for-bit for finite w, so only non-zero (or non-finite) emission needs the add */
+		const bool emits = !(m.emission[0] == 0.0f && m.emission[1] == 0.0f && m.emission[2] == 0.0f);
+		d.flags = (uv ? 1u : 0u) | (emits ? 2u : 0u);
+		mats[i] = d;
+	}
+
+	/* BVHs → pair nodes; triangles in leaf order */
+	std::vector<PairNode> pairs;
+	std::vector<DevBvh> bvhs(f->bvh_count);
+	std::vector<PackedTri> tris;
+	std::vector<uint32_t> slot_poly;
+	std::vector<int32_t> top_prims;
+	std::vector<uint32_t> mesh_of_bvh(f->bvh_count, 0xffffffffu);
+	for (uint32_t m = 0; m < f->mesh_count; ++m) {
+		if (f->meshes[m].bvh >= f->bvh_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "mesh bvh index out of range"); }
+		mesh_of_bvh[f->meshes[m].bvh] = m;
+	}
+	for (uint32_t b = 0; b < f->bvh_count; ++b) {
+		const crs_bvh &src = f->bvhs[b];
+		if ((uint64_t)src.node_offset + src.node_count > f->bvh_node_count || (uint64_t)src.prim_offset + src.prim_count > f->prim_index_count) {
+			crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u ranges out of bounds", b);
+		}
+		if (b == f->top_bvh) {
+			FAIL_IF(build_pairs(f, src, pairs, bvhs[b], (uint32_t)top_prims.size()));
+			for (uint32_t i = 0; i < src.prim_count; ++i) {
+				const int32_t inst = f->prim_indices[src.prim_offset + i];
+				if (inst < 0 || (uint32_t)inst >= f->instance_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "top-level prim index out of range"); }
+				top_prims.push_back(inst);
+			}
+			continue;
+		}
+		const uint32_t m = mesh_of_bvh[b];
+		if (m == 0xffffffffu) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u belongs to no mesh", b); }
+		const crs_mesh &mesh = f->meshes[m];
+		FAIL_IF(build_pairs(f, src, pairs, bvhs[b], (uint32_t)tris.size()));
+		for (uint32_t i = 0; i < src.prim_count; ++i) {
+			const int32_t local = f->prim_indices[src.prim_offset + i];
+			if (local < 0 || (uint32_t)local >= mesh.poly_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "prim index out of range"); }
+			const uint32_t poly = mesh.poly_offset + (uint32_t)local;
+			const crs_poly &p = f->polys[poly];
+			for (int k = 0; k < 3; ++k)
+				if (p.v[k] < 0 || (uint32_t)p.v[k] >= f->vertex_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "vertex index out of range"); }
+			float v0[3], v1[3], v2[3];
+			f3(v0, f->vertices, (size_t)p.v[0]); f3(v1, f->vertices, (size_t)p.v[1]); f3(v2, f->vertices, (size_t)p.v[2]);
+			PackedTri t;
+			/* poly.c:20-22 — plain fp32 ops; this TU is compiled without contraction on the host side */
+			for (int k = 0; k < 3; ++k) { t.v0[k] = v0[k]; t.e1[k] = v0[k] - v1[k]; t.e2[k] = v2[k] - v0[k]; }
+			volatile float m0 = t.e1[1] * t.e2[2], m1 = t.e1[2] * t.e2[1], m2 = t.e1[2] * t.e2[0], m3 = t.e1[0] * t.e2[2],
+						   m4 = t.e1[0] * t.e2[1], m5 = t.e1[1] * t.e2[0];
+			t.n[0] = m0 - m1; t.n[1] = m2 - m3; t.n[2] = m4 - m5;
+			tris.push_back(t);
+			slot_poly.push_back(poly);
+		}
+	}
+
+	/* per-poly shading records */
+	std::vector<ShadePoly> spolys(f->poly_count);
+	for (uint32_t m = 0; m < f->mesh_count; ++m) {
+		const crs_mesh &mesh = f->meshes[m];
+		if ((uint64_t)mesh.poly_offset + mesh.poly_count > f->poly_count || (uint64_t)mesh.material_offset + mesh.material_count > f->material_count) {
+			crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "mesh %u ranges out of bounds", m);
+		}
+		for (uint32_t i = 0; i < mesh.poly_count; ++i) {
+			const crs_poly &p = f->polys[mesh.poly_offset + i];
+			ShadePoly sp;
+			memset(&sp, 0, sizeof sp);
+			bool has_n = p.has_normals != 0;
+			for (int k = 0; k < 3 && has_n; ++k) if (p.n[k] < 0 || (uint32_t)p.n[k] >= f->normal_count) has_n = false;
+			if (has_n) {
+				f3(sp.n0, f->normals, (size_t)p.n[0]); f3(sp.n1, f->normals, (size_t)p.n[1]); f3(sp.n2, f->normals, (size_t)p.n[2]);
+			} else if (p.has_normals) {
+				crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "normal index out of range");
+			} else {
+				/* geometric normal e1 x e2 (poly.c:22,46), same operations as above */
+				float v0[3], v1[3], v2[3], e1[3], e2[3];
+				f3(v0, f->vertices, (size_t)p.v[0]); f3(v1, f->vertices, (size_t)p.v[1]); f3(v2, f->vertices, (size_t)p.v[2]);
+				for (int k = 0; k < 3; ++k) { e1[k] = v0[k] - v1[k]; e2[k] = v2[k] - v0[k]; }
+				volatile float m0 = e1[1] * e2[2], m1 = e1[2] * e2[1], m2 = e1[2] * e2[0], m3 = e1[0] * e2[2], m4 = e1[0] * e2[1], m5 = e1[1] * e2[0];
+				sp.n0[0] = m0 - m1; sp.n0[1] = m2 - m3; sp.n0[2] = m4 - m5;
+			}
+			bool has_uv = mesh.texcoord_count != 0 && p.t[0] != -1;                          /* instance.c:151-153 */
+			if (has_uv) {
+				for (int k = 0; k < 3; ++k)
+					if (p.t[k] < 0 || (uint32_t)p.t[k] >= f->texcoord_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "texcoord index out of range"); }
+				sp.t0[0] = f->texcoords[2 * (size_t)p.t[0]]; sp.t0[1] = f->texcoords[2 * (size_t)p.t[0] + 1];
+				sp.t1[0] = f->texcoords[2 * (size_t)p.t[1]]; sp.t1[1] = f->texcoords[2 * (size_t)p.t[1] + 1];
+				sp.t2[0] = f->texcoords[2 * (size_t)p.t[2]]; sp.t2[1] = f->texcoords[2 * (size_t)p.t[2] + 1];
+			}
+			if (p.material >= mesh.material_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "poly material index out of range"); }
+			sp.material = mesh.material_offset + p.material;
+			sp.flags = (has_n ? 1u : 0u) | (has_uv ? 2u : 0u);
+			spolys[mesh.poly_offset + i] = sp;
+		}
+	}
+
+	/* instances */
+	std::vector<DevInstance> insts(f->instance_count);
+	for (uint32_t i = 0; i < f->instance_count; ++i) {
+		const crs_instance &src = f->instances[i];
+		DevInstance d;
+		memset(&d, 0, sizeof d);
+		memcpy(d.Ainv, src.Ainv, sizeof d.Ainv);
+		memcpy(d.A, src.A, sizeof d.A);
+		d.kind = src.kind;
+		if (src.kind == CRS_INST_MESH) {
+			if (src.object >= f->mesh_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "instance mesh index out of range"); }
+			d.bvh = f->meshes[src.object].bvh;
+			d.ray_offset = f->meshes[src.object].ray_offset;
+		} else if (src.kind == CRS_INST_SPHERE) {
+			if (src.object >= f->sphere_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "instance sphere index out of range"); }
+			d.ray_offset = f->spheres[src.object].ray_offset;
+			d.radius = f->spheres[src.object].radius;
+			d.material = f->spheres[src.object].material;
+			if (d.material >= f->material_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "sphere material out of range"); }
+		} else { crgpu_scene_destroy(s); return fail(CRGPU_ERR_UNSUPPORTED, "instance kind %u (volumes are not reachable from the scene loader)", src.kind); }
+		insts[i] = d;
+	}
+
+	/* textures */
+	uint8_t *texdata = nullptr;
+	if (f->texdata_bytes) {
+		CUS(cudaMalloc((void **)&texdata, (size_t)f->texdata_bytes));
+		s->allocs.push_back(texdata);
+		CUS(cudaMemcpy(texdata, f->texdata, (size_t)f->texdata_bytes, cudaMemcpyHostToDevice));
+	}
+	std::vector<DevTexture> texs(f->texture_count);
+	for (uint32_t i = 0; i < f->texture_count; ++i) {
+		const crs_texture &t = f->textures[i];
+		const uint64_t bytes = (uint64_t)t.width * t.height * t.channels * (t.is_float ? 4u : 1u);
+		if (t.width == 0 || t.height == 0 || t.channels == 0 || t.channels > 4 || t.data_offset + bytes > f->texdata_bytes) {
+			crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "texture %u malformed", i);
+		}
+		DevTexture d;
+		d.width = t.width; d.height = t.height; d.channels = t.channels; d.is_float = t.is_float; d.has_alpha = t.has_alpha; d.pad = 0;
+		d.data = texdata + t.data_offset;
+		texs[i] = d;
+	}
+	for (uint32_t i = 0; i < f->node_count; ++i)
+		if (f->nodes[i].kind == CRS_COLOR_IMAGE && f->nodes[i].tex >= (int32_t)f->texture_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "node %u texture index out of range", i); }
+	std::vector<crs_node> nodes(f->nodes, f->nodes + f->node_count);
+
+	DevScene &d = s->dev;
+	d.cam.sensor_x = f->camera.sensor_x; d.cam.sensor_y = f->camera.sensor_y;
+	d.cam.aperture = f->camera.aperture; d.cam.focal_distance = f->camera.focal_distance;
+	memcpy(d.cam.forward, f->camera.forward, 12); memcpy(d.cam.right, f->camera.right, 12); memcpy(d.cam.up, f->camera.up, 12);
+	d.cam.width = f->camera.width; d.cam.height = f->camera.height;
+	memcpy(d.cam.A, f->camera.A, sizeof d.cam.A);
+	d.image_width = f->prefs.image_width; d.image_height = f->prefs.image_height;
+	d.sample_count = f->prefs.sample_count; d.bounces = f->prefs.bounces;
+	d.background = f->background;
+	d.instance_count = f->instance_count;
+	d.top = bvhs[f->top_bvh];
+	FAIL_IF(upload(s, pairs, &d.pairs));
+	FAIL_IF(upload(s, tris, &d.tris));
+	FAIL_IF(upload(s, slot_poly, &d.slot_poly));
+	FAIL_IF(upload(s, spolys, &d.spolys));
+	FAIL_IF(upload(s, top_prims, &d.top_prims));
+	FAIL_IF(upload(s, bvhs, &d.bvhs));
+	FAIL_IF(upload(s, insts, &d.instances));
+	FAIL_IF(upload(s, mats, &d.materials));
+	FAIL_IF(upload(s, nodes, &d.nodes));
+	FAIL_IF(upload(s, texs, &d.textures));
+
+	CUS(cudaMalloc((void **)&s->dev_copy, sizeof(DevScene)));
+	s->allocs.push_back(s->dev_copy);
+	CUS(cudaMemcpy(s->dev_copy, &s->dev, sizeof(DevScene), cudaMemcpyHostToDevice));
+	s->fb_floats = (size_t)d.image_width * d.image_height * 3u;
+	CUS(cudaMalloc((void **)&s->fb, s->fb_floats * sizeof(float)));
+	CUS(cudaMemset(s->fb, 0, s->fb_floats * sizeof(float)));
+	CUS(cudaMalloc((void **)&s->wb.counts, 2 * sizeof(unsigned)));
+	CUS(cudaMalloc((void **)&s->wb.stats, 8 * sizeof(unsigned long long)));
+	CUS(cudaDeviceSynchronize());
+#undef FAIL_IF
+#undef CUS
+	*out = s;
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_set_max_paths_in_flight(crgpu_scene *s, uint64_t max_paths) {
+	if (!s || max_paths < 1024) return fail(CRGPU_ERR_BAD_ARGUMENT, "max_paths must be >= 1024");
+	if (max_paths > (1ull << 31)) return fail(CRGPU_ERR_BAD_ARGUMENT, "max_paths must be <= 2^31");
+	s->max_paths = max_paths;
+	return CRGPU_OK;
+}
+
+static int check_rect(const crgpu_scene *s, int x0, int y0, int x1, int y1) {
+	if (x0 < 0 || y0 < 0 || x1 > (int)s->dev.image_width || y1 > (int)s->dev.image_height || x1 <= x0 || y1 <= y0)
+		return fail(CRGPU_ERR_BAD_ARGUMENT, "tile [%d,%d)x[%d,%d) outside the %ux%u image", x0, x1, y0, y1, s->dev.image_width, s->dev.image_height);
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1, int pass_begin, int pass_count,
+								 unsigned flags, struct crgpu_stats *stats) {
+	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
+	int rc = check_rect(s, x0, y0, x1, y1);
+	if (rc) return rc;
+	if (pass_begin < 0 || pass_count < 0 || (uint64_t)pass_begin + (uint64_t)pass_count > s->dev.sample_count)
+		return fail(CRGPU_ERR_BAD_ARGUMENT, "passes [%d,%d) outside [0,%u)", pass_begin, pass_begin + pass_count, s->dev.sample_count);
+	CU(cudaSetDevice(s->device));
+	const int tw = x1 - x0, th = y1 - y0;
+	const uint64_t tile_pixels = (uint64_t)tw * (uint64_t)th;
+	if (tile_pixels > s->max_paths) return fail(CRGPU_ERR_BAD_ARGUMENT, "tile has %llu pixels > max paths in flight %llu: use smaller tiles or raise the limit",
+												(unsigned long long)tile_pixels, (unsigned long long)s->max_paths);
+	uint64_t batch = s->max_paths / tile_pixels;
+	if (batch > (uint64_t)pass_count) batch = (uint64_t)pass_count;
+	if (batch < 1) batch = 1;
+	rc = alloc_wave(s, tile_pixels * batch);
+	if (rc) return rc;
+
+	cudaStream_t st = s->stream;
+	const bool count = (flags & CRGPU_FLAG_COUNT) != 0;
+	const bool timing = (flags & CRGPU_FLAG_TIME_KERNELS) != 0;
+	const int maxDepth = (int)s->dev.bounces;
+	const int grid = s->sm_count * 8;
+	uint64_t launches = 0;
+	float trace_ms = 0.f, shade_ms = 0.f;
+	CU(cudaMemsetAsync(s->wb.stats, 0, 8 * sizeof(unsigned long long), st));
+	if (timing) CU(cudaEventRecord(s->ev[0], st));
+	std::vector<cudaEvent_t> tev;   /* per-kernel events when timing */
+	for (int pb = pass_begin; pb < pass_begin + pass_count; pb += (int)batch) {
+		TileDesc td;
+		td.x0 = x0; td.y0 = y0; td.tw = tw; td.th = th;
+		td.pass_begin = pb;
+		td.pass_count = (pass_begin + pass_count - pb) < (int)batch ? (pass_begin + pass_count - pb) : (int)batch;
+		crg_launch_generate(s->dev, s->wb, td, grid, st); ++launches;
+		int cur = 0;
+		for (int depth = 0; depth < maxDepth; ++depth) {
+			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
+			crg_launch_trace(s->dev, s->wb, cur, count, grid, st);
+			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
+			crg_launch_shade(s->dev_copy, s->wb, cur, depth, maxDepth, grid, st);
+			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
+			launches += 2;
+			cur ^= 1;
+		}
+		crg_launch_accumulate(s->fb, s->wb.L, td, (int)s->dev.image_width, (int)s->dev.image_height, grid, st); ++launches;
+	}
+	if (timing) CU(cudaEventRecord(s->ev[1], st));
+	CU(cudaGetLastError());
+	unsigned long long h[8];
+	CU(cudaMemcpyAsync(h, s->wb.stats, sizeof h, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	float total_ms = 0.f;
+	if (timing) {
+		cudaEventElapsedTime(&total_ms, s->ev[0], s->ev[1]);
+		for (size_t i = 0; i + 3 <= tev.size(); i += 3) {
+			float a = 0.f, b = 0.f;
+			cudaEventElapsedTime(&a, tev[i], tev[i + 1]);
+			cudaEventElapsedTime(&b, tev[i + 1], tev[i + 2]);
+			trace_ms += a; shade_ms += b;
+		}
+		for (cudaEvent_t e : tev) cudaEventDestroy(e);
+	}
+	if (stats) {
+		memset(stats, 0, sizeof *stats);
+		stats->paths = tile_pixels * (uint64_t)pass_count;
+		stats->rays = h[0]; stats->node_pairs = h[1]; stats->tri_tests = h[2]; stats->sphere_tests = h[3]; stats->inst_visits = h[4];
+		stats->kernel_launches = launches;
+		stats->trace_ms = trace_ms; stats->shade_ms = shade_ms; stats->total_ms = total_ms;
+	}
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_framebuffer_clear(crgpu_scene *s) {
+	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
+	CU(cudaSetDevice(s->device));
+	CU(cudaMemsetAsync(s->fb, 0, s->fb_floats * sizeof(float), s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	return CRGPU_OK;
+}
+
+static int fb_copy(crgpu_scene *s, float *host, int x0, int y0, int x1, int y1, bool to_host) {
+	if (!s || !host) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
+	CU(cudaSetDevice(s->device));
+	const size_t W = s->dev.image_width, H = s->dev.image_height;
+	if (x1 <= x0) { x0 = 0; y0 = 0; x1 = (int)W; y1 = (int)H; }
+	int rc = check_rect(s, x0, y0, x1, y1);
+	if (rc) return rc;
+	/* rows y0..y1-1 (y up) are storage rows H-y1 .. H-1-y0 */
+	const size_t row0 = H - (size_t)y1, rows = (size_t)(y1 - y0);
+	const size_t off = (row0 * W + (size_t)x0) * 3u;
+	const size_t pitch = W * 3u * sizeof(float), width = (size_t)(x1 - x0) * 3u * sizeof(float);
+	if (to_host) CU(cudaMemcpy2DAsync(host + off, pitch, s->fb + off, pitch, width, rows, cudaMemcpyDeviceToHost, s->stream));
+	else CU(cudaMemcpy2DAsync(s->fb + off, pitch, host + off, pitch, width, rows, cudaMemcpyHostToDevice, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	return CRGPU_OK;
+}
+extern "C" int crgpu_framebuffer_read(crgpu_scene *s, float *host_rgb, int x0, int y0, int x1, int y1) {
+	return fb_copy(s, host_rgb, x0, y0, x1, y1, true);
+}
+extern "C" int crgpu_framebuffer_write(crgpu_scene *s, const float *host_rgb, int x0, int y0, int x1, int y1) {
+	return fb_copy(s, const_cast<float *>(host_rgb), x0, y0, x1, y1, false);
+}
+
+extern "C" int crgpu_framebuffer_to_srgb8(crgpu_scene *s, uint8_t *host_rgb8) {
+	if (!s || !host_rgb8) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
+	CU(cudaSetDevice(s->device));
+	if (!s->fb8) CU(cudaMalloc((void **)&s->fb8, s->fb_floats));
+	crg_launch_to_srgb8(s->fb, s->fb8, s->fb_floats, s->sm_count * 8, s->stream);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(host_rgb8, s->fb8, s->fb_floats, cudaMemcpyDeviceToHost, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_framebuffer_device_ptr(crgpu_scene *s, void **dev_ptr, size_t *bytes) {
+	if (!s || !dev_ptr) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
+	*dev_ptr = s->fb;
+	if (bytes) *bytes = s->fb_floats * sizeof(float);
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_trace_kat(crgpu_scene *s, const int32_t *xyp, int count, void *records_out) {
+	if (!s || !xyp || !records_out || count < 0) return fail(CRGPU_ERR_BAD_ARGUMENT, "bad argument");
+	if (count == 0) return CRGPU_OK;
+	CU(cudaSetDevice(s->device));
+	int32_t *dx = nullptr;
+	void *dk = nullptr;
+	CU(cudaMalloc((void **)&dx, (size_t)count * 3 * sizeof(int32_t)));
+	CU(cudaMalloc((void **)&dk, (size_t)count * CRG_HITKAT_BYTES));
+	CU(cudaMemcpyAsync(dx, xyp, (size_t)count * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+	crg_launch_kat(s->dev_copy, dx, count, dk, s->stream);
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(records_out, dk, (size_t)count * CRG_HITKAT_BYTES, cudaMemcpyDeviceToHost, s->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+	cudaFree(dx); cudaFree(dk);
+	if (e != cudaSuccess) return fail(CRGPU_ERR_CUDA, "trace_kat: %s", cudaGetErrorString(e));
+	return CRGPU_OK;
+}

@@ -1,0 +1,174 @@
+/*
+ * crgpu_shade.cu — K3 (shade + compaction), K5 (accumulate), sRGB8 conversion and the known-answer
+ * kernel: see crgpu_wave.cuh.  The node interpreter and the fp64 libm stand-ins are real function
+ * calls (__noinline__), so the scene descriptor is read through a pointer to its device copy.
+ */
+#include "crgpu_wave.cuh"
+#include "crgpu_shade.cuh"
+
+/* ---- K3 (+K4 compaction) ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth) {
+	const DevScene &sc = *scp;
+	const unsigned n = wb.counts[cur];
+	const int nxt = cur ^ 1;
+	const unsigned lane = threadIdx.x & 31u;
+	/* whole warps iterate together so the ballot below is convergent */
+	const unsigned stride = gridDim.x * blockDim.x;
+	const unsigned nround = (n + 31u) & ~31u;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+		bool alive = false;
+		v3 p_next = v3make(0, 0, 0), d_next = v3make(0, 0, 0);
+		float wr = 0.f, wg = 0.f, wbl = 0.f;
+		unsigned id = 0u;
+		uint64_t rng = 0ull;
+		if (i < n) {
+			const float4 a = wb.stA[cur][i];
+			const float4 b = wb.stB[cur][i];
+			const uint4 c = wb.stC[cur][i];
+			const float4 hq = wb.hit[i];
+			Hit hit;
+			hit.t = hq.x; hit.u = hq.y; hit.v = hq.z; hit.prim = __float_as_uint(hq.w);
+			hit.inst = wb.hitInst[i];
+			const v3 o = v3make(a.x, a.y, a.z), d = v3make(a.w, b.x, b.y);
+			wr = b.z; wg = b.w; wbl = __uint_as_float(c.x);
+			id = c.y;
+			rng = (uint64_t)c.z | ((uint64_t)c.w << 32);
+			if (hit.inst < 0) {                                                               /* pathtrace.c:39-42 */
+				const col4 bg = cr_sample_background(sc, d);
+				float4 L = wb.L[id];
+				L.x = L.x + wr * bg.r; L.y = L.y + wg * bg.g; L.z = L.z + wbl * bg.b;
+				wb.L[id] = L;
+			} else {
+				Rec rec;
+				const int material = cr_reconstruct_hit(sc, o, d, hit, rec, false);
+				const DevMaterial mat = sc.materials[material];
+				if (mat.flags & 2u) {                                                         /* pathtrace.c:44 (x+0 == x) */
+					float4 L = wb.L[id];
+					L.x = L.x + wr * mat.emission[0]; L.y = L.y + wg * mat.emission[1]; L.z = L.z + wbl * mat.emission[2];
+					wb.L[id] = L;
+				}
+				if (depth + 1 < maxDepth) {                                                   /* else: loop ends, sample unused */
+					const BsdfSample s = cr_sample_bsdf(sc, mat.bsdf, rng, rec);             /* pathtrace.c:46-48 */
+					float probability = 1.0f;
+					bool cont = true;
+					if (depth >= 4) {                                                         /* pathtrace.c:50-55 */
+						probability = CR_MAX(s.color.r, CR_MAX(s.color.g, s.color.b));
+						if (cr_draw(rng) > probability) cont = false;
+					}
+					if (cont) {
+						const float inv = cr_div(1.0f, probability);                          /* pathtrace.c:57 */
+						wr = (s.color.r * wr) * inv; wg = (s.color.g * wg) * inv; wbl = (s.color.b * wbl) * inv;
+						p_next = rec.p; d_next = s.out;
+						alive = true;
+					}
+				}
+			}
+		}
+		/* K4: order-preserving warp compaction, one atomic per warp */
+		const unsigned mask = __ballot_sync(0xffffffffu, alive);
+		if (mask) {
+			unsigned base = 0u;
+			if (lane == 0u) base = atomicAdd(&wb.counts[nxt], (unsigned)__popc(mask));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (alive) {
+				const unsigned j = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+				wb.stA[nxt][j] = make_float4(p_next.x, p_next.y, p_next.z, d_next.x);
+				wb.stB[nxt][j] = make_float4(d_next.y, d_next.z, wr, wg);
+				wb.stC[nxt][j] = make_uint4(__float_as_uint(wbl), id, (unsigned)(rng & 0xffffffffull), (unsigned)(rng >> 32));
+			}
+		}
+	}
+}
+
+/* ---- K5 ------------------------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) k_accumulate(float *__restrict__ fb, const float4 *__restrict__ L, TileDesc td,
+													 int image_width, int image_height) {
+	const unsigned tile_pixels = (unsigned)(td.tw * td.th);
+	for (unsigned px = blockIdx.x * blockDim.x + threadIdx.x; px < tile_pixels; px += gridDim.x * blockDim.x) {
+		const int x = td.x0 + (int)(px % (unsigned)td.tw);
+		const int y = td.y0 + (int)(px / (unsigned)td.tw);
+		float *dst = fb + ((size_t)x + (size_t)(image_height - (y + 1)) * (size_t)image_width) * 3u;  /* texture.c:24-28 */
+		float r = dst[0], g = dst[1], b = dst[2];
+		for (int pl = 0; pl < td.pass_count; ++pl) {
+			const float4 s = L[(size_t)pl * tile_pixels + px];
+			const int completed = td.pass_begin + pl + 1;                                     /* renderer.c:288-291 */
+			const float k = (float)(completed - 1);
+			const float t = cr_div(1.0f, (float)completed);
+			r = (r * k + s.x) * t; g = (g * k + s.y) * t; b = (b * k + s.z) * t;
+		}
+		dst[0] = r; dst[1] = g; dst[2] = b;
+	}
+}
+
+/* colorToSRGB + setPixel(char_p): renderer.c:297-300, texture.c:19-21 */
+__global__ void k_to_srgb8(const float *__restrict__ fb, uint8_t *__restrict__ out, size_t n) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const float c = cr_linear_to_srgb(fb[i]);
+		const float s = CR_MIN(c * 255.0f, 255.0f);
+		/* (unsigned char) of a negative/NaN float is UB in C; x86 cvttss2si + truncation gives the low byte */
+		out[i] = (uint8_t)(cr_f2i(s) & 0xff);
+	}
+}
+
+/* ---- known-answer kernel (parity tests): one thread per (x, y, pass) ---------------------------------------------------------- */
+struct HitKat {
+	int32_t x, y, pixIdx, instIndex, polyIndex;
+	float o[3], d[3];
+	float distance, uv[2];
+	float hitPoint[3], normal[3];
+	float emission[3];
+	float out[3], color[4];
+	float nextDraw;
+	float pad[9];
+};
+
+__global__ void k_kat(const DevScene *__restrict__ scp, const int32_t *__restrict__ xyp, int count, HitKat *__restrict__ outv) {
+	const DevScene &sc = *scp;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	HitKat k;
+	memset(&k, 0, sizeof k);
+	const int x = xyp[3 * i], y = xyp[3 * i + 1], pass = xyp[3 * i + 2];
+	k.x = x; k.y = y; k.pixIdx = y * (int)sc.image_width + x;
+	uint64_t rng = cr_rng_init((uint32_t)k.pixIdx, (uint32_t)pass, sc.sample_count);
+	v3 o, d;
+	cr_camera_ray(sc.cam, x, y, rng, o, d);
+	k.o[0] = o.x; k.o[1] = o.y; k.o[2] = o.z; k.d[0] = d.x; k.d[1] = d.y; k.d[2] = d.z;
+	const Hit hit = cr_closest_hit<false>(sc, o, d, nullptr);
+	k.instIndex = hit.inst;
+	BsdfSample s;
+	if (hit.inst < 0) {
+		k.polyIndex = -1;
+		s.out = v3make(0.f, 0.f, 0.f);
+		s.color = cr_sample_background(sc, d);
+	} else {
+		Rec rec;
+		const int material = cr_reconstruct_hit(sc, o, d, hit, rec, true);
+		const DevInstance *inst = sc.instances + hit.inst;
+		k.polyIndex = inst->kind == CRS_INST_MESH ? (int)sc.slot_poly[hit.prim] : -1;
+		k.distance = hit.t; k.uv[0] = rec.uv.x; k.uv[1] = rec.uv.y;
+		k.hitPoint[0] = rec.p.x; k.hitPoint[1] = rec.p.y; k.hitPoint[2] = rec.p.z;
+		k.normal[0] = rec.n.x; k.normal[1] = rec.n.y; k.normal[2] = rec.n.z;
+		const DevMaterial mat = sc.materials[material];
+		k.emission[0] = mat.emission[0]; k.emission[1] = mat.emission[1]; k.emission[2] = mat.emission[2];
+		s = cr_sample_bsdf(sc, mat.bsdf, rng, rec);
+	}
+	k.out[0] = s.out.x; k.out[1] = s.out.y; k.out[2] = s.out.z;
+	k.color[0] = s.color.r; k.color[1] = s.color.g; k.color[2] = s.color.b; k.color[3] = s.color.a;
+	k.nextDraw = cr_draw(rng);
+	outv[i] = k;
+}
+
+void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int grid, cudaStream_t st) {
+	k_shade<<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
+}
+void crg_launch_accumulate(float *fb, const float4 *L, const TileDesc &td, int W, int H, int grid, cudaStream_t st) {
+	k_accumulate<<<grid, 256, 0, st>>>(fb, L, td, W, H);
+}
+void crg_launch_to_srgb8(const float *fb, uint8_t *out, size_t n, int grid, cudaStream_t st) {
+	k_to_srgb8<<<grid, 256, 0, st>>>(fb, out, n);
+}
+void crg_launch_kat(const DevScene *dsc, const int32_t *xyp, int count, void *out, cudaStream_t st) {
+	k_kat<<<(count + 63) / 64, 64, 0, st>>>(dsc, xyp, count, static_cast<HitKat *>(out));
+}
+static_assert(sizeof(HitKat) == 160, "HitKat must match struct hit_kat of oracle/ref_harness.c");

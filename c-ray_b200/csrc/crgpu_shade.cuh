@@ -1,0 +1,455 @@
+/*
+ * crgpu_shade.cuh — hit reconstruction, node-graph evaluation and BSDF sampling (device functions).
+ *
+ * Restates:
+ *   intersectSphere / intersectMesh (the post-hit half)   reference src/datatypes/instance.c:33-60,150-185
+ *   poly.c:40-47 (barycentric normal), sphere.c:52-61
+ *   textureGetPixel / Internal                             src/datatypes/image/texture.c:32-79
+ *   color / value nodes                                    src/nodes/textures/{constant,image,checker,gradient,alpha}.c,
+ *                                                          src/nodes/converter/{grayscale,blackbody}.c, src/nodes/valuenode.c
+ *   bsdf nodes                                             src/nodes/shaders/{diffuse,metal,glass,plastic,mix,add,
+ *                                                          transparent,emission,background,isotropic}.c
+ *
+ * The reference evaluates the graph through recursive function pointers.  Here the graph is a flat
+ * table (crs_node) walked by a small interpreter: MIX and PLASTIC are tail calls (a loop), ADD uses an
+ * explicit 4-entry operand stack, color<->value recursion is bounded at compile time (depth 3; deeper
+ * graphs are rejected at upload with CRGPU_ERR_UNSUPPORTED).  Draw order is the reference's.
+ */
+#pragma once
+#include "crgpu_math.cuh"
+#include "crgpu_scene.cuh"
+#include "crgpu_trace.cuh"
+
+#ifndef CRG_NODE_DEPTH
+#define CRG_NODE_DEPTH 3      /* color->value->color nesting supported by the interpreter */
+#define CRG_ADD_STACK 4
+#endif
+
+struct Rec {                  /* the fields of struct hitRecord (hitrecord.h:14-23) the nodes read */
+	v3 inc_d;                 /* incident.direction */
+	v3 p, n;                  /* hitPoint, surfaceNormal */
+	v2 uv;
+	float IOR;                /* material.IOR */
+};
+
+struct BsdfSample { v3 out; col4 color; };
+
+/* ---- texture.c:32-63 ------------------------------------------------------------------------------------------ */
+CRD col4 cr_texel(const DevTexture &t, uint64_t x, uint64_t y) {
+	x = x % t.width;
+	y = y % t.height;
+	const size_t idx = (size_t)((x + ((uint64_t)(t.height - 1) - y) * t.width) * t.channels);
+	col4 o;
+	if (t.channels == 1) {
+		if (t.is_float) o.r = __ldg(reinterpret_cast<const float *>(t.data) + idx);
+		else o.r = cr_div((float)__ldg(t.data + idx), 255.0f);
+		o.g = o.r; o.b = o.r; o.a = 1.0f;
+	} else if (t.is_float) {
+		const float *f = reinterpret_cast<const float *>(t.data);
+		o.r = __ldg(f + idx); o.g = __ldg(f + idx + 1); o.b = __ldg(f + idx + 2);
+		o.a = t.has_alpha ? __ldg(f + idx + 3) : 1.0f;
+	} else if (t.channels == 4) {
+		const uchar4 px = __ldg(reinterpret_cast<const uchar4 *>(t.data + idx));
+		o.r = cr_div((float)px.x, 255.0f); o.g = cr_div((float)px.y, 255.0f); o.b = cr_div((float)px.z, 255.0f);
+		o.a = cr_div((float)px.w, 255.0f);
+	} else {
+		o.r = cr_div((float)__ldg(t.data + idx), 255.0f);
+		o.g = cr_div((float)__ldg(t.data + idx + 1), 255.0f);
+		o.b = cr_div((float)__ldg(t.data + idx + 2), 255.0f);
+		o.a = t.has_alpha ? cr_div((float)__ldg(t.data + idx + 3), 255.0f) : 1.0f;
+	}
+	return o;
+}
+
+/* alpha lane only (same arithmetic as cr_texel().a) */
+CRD float cr_texel_alpha(const DevTexture &t, uint64_t x, uint64_t y) {
+	if (!t.has_alpha || t.channels != 4) return 1.0f;
+	x = x % t.width;
+	y = y % t.height;
+	const size_t idx = (size_t)((x + ((uint64_t)(t.height - 1) - y) * t.width) * 4u);
+	if (t.is_float) return __ldg(reinterpret_cast<const float *>(t.data) + idx + 3);
+	return cr_div((float)__ldg(t.data + idx + 3), 255.0f);
+}
+
+CRD col4 cr_texture_get(const DevTexture &t, float x, float y, bool filtered) {             /* texture.c:66-79 */
+	if (!filtered) return cr_texel(t, cr_f2sz(x), cr_f2sz(y));
+	x = x * (float)t.width;
+	y = y * (float)t.height;
+	const float xcopy = x - 0.5f;
+	const float ycopy = y - 0.5f;
+	const int xint = cr_f2i(xcopy);
+	const int yint = cr_f2i(ycopy);
+	const col4 tl = cr_texel(t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)yint);
+	const col4 tr = cr_texel(t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)yint);
+	const col4 bl = cr_texel(t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)(yint + 1));
+	const col4 br = cr_texel(t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)(yint + 1));
+	const float fx = xcopy - (float)xint, fy = ycopy - (float)yint;
+	return c4mix(c4mix(tl, tr, fx), c4mix(bl, br, fx), fy);
+}
+
+CRD float cr_texture_get_alpha(const DevTexture &t, float x, float y, bool filtered) {
+	if (!filtered) return cr_texel_alpha(t, cr_f2sz(x), cr_f2sz(y));
+	x = x * (float)t.width;
+	y = y * (float)t.height;
+	const float xcopy = x - 0.5f;
+	const float ycopy = y - 0.5f;
+	const int xint = cr_f2i(xcopy);
+	const int yint = cr_f2i(ycopy);
+	const float tl = cr_texel_alpha(t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)yint);
+	const float tr = cr_texel_alpha(t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)yint);
+	const float bl = cr_texel_alpha(t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)(yint + 1));
+	const float br = cr_texel_alpha(t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)(yint + 1));
+	const float fx = xcopy - (float)xint, fy = ycopy - (float)yint;
+	const float top = tl * (1.0f - fx) + tr * fx;
+	const float bot = bl * (1.0f - fx) + br * fx;
+	return top * (1.0f - fy) + bot * fy;
+}
+
+/* ---- color / value nodes ------------------------------------------------------------------------------------------ */
+template <int D> struct NodeEval {
+	static __device__ __noinline__ col4 color(const DevScene &sc, int node, const Rec &rec);
+	static __device__ __noinline__ float value(const DevScene &sc, int node, const Rec &rec);
+	static __device__ __noinline__ float alpha(const DevScene &sc, int node, const Rec &rec);
+};
+
+static __device__ __noinline__ col4 cr_image_color(const DevScene &sc, const crs_node &n, const Rec &rec) {            /* image.c:31-48 */
+	if (n.tex < 0) return c4make(1.0f, 0.0f, 0.5f, 1.0f);
+	const DevTexture t = sc.textures[n.tex];
+	col4 out;
+	if (n.options & CRS_IMG_NO_BILINEAR) {
+		const float x = rec.uv.x * (float)t.width;
+		const float y = rec.uv.y * (float)t.height;
+		out = cr_texture_get(t, x, y, false);
+	} else {
+		out = cr_texture_get(t, rec.uv.x, rec.uv.y, true);
+	}
+	if (n.options & CRS_IMG_SRGB_TRANSFORM)
+		out = c4make(cr_srgb_to_linear(out.r), cr_srgb_to_linear(out.g), cr_srgb_to_linear(out.b), out.a);
+	return out;
+}
+
+static __device__ __noinline__ float cr_image_alpha(const DevScene &sc, const crs_node &n, const Rec &rec) {
+	if (n.tex < 0) return 1.0f;
+	const DevTexture t = sc.textures[n.tex];
+	if (n.options & CRS_IMG_NO_BILINEAR)
+		return cr_texture_get_alpha(t, rec.uv.x * (float)t.width, rec.uv.y * (float)t.height, false);
+	return cr_texture_get_alpha(t, rec.uv.x, rec.uv.y, true);
+}
+
+CRD col4 cr_gradient(const crs_node &n, const Rec &rec) {                                   /* gradient.c:40-45 */
+	const v3 unit = v3norm(rec.inc_d);
+	const float t = 0.5f * (unit.y + 1.0f);
+	return c4add(c4coef(1.0f - t, c4make(n.f[0], n.f[1], n.f[2], n.f[3])), c4coef(t, c4make(n.f[4], n.f[5], n.f[6], n.f[7])));
+}
+
+template <int D>
+__device__ __noinline__ col4 NodeEval<D>::color(const DevScene &sc, int node, const Rec &rec) {
+	while (true) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_COLOR_CONSTANT: return c4make(n.f[0], n.f[1], n.f[2], n.f[3]);             /* constant.c:39-42 */
+		case CRS_COLOR_IMAGE: return cr_image_color(sc, n, rec);
+		case CRS_COLOR_GRADIENT: return cr_gradient(n, rec);
+		case CRS_COLOR_CHECKER: {                                                           /* checker.c:31-54 */
+			const float coef = NodeEval<D - 1>::value(sc, n.in[2], rec);
+			float sines;
+			if (rec.uv.x >= 0) sines = cr_sinf(coef * rec.uv.x) * cr_sinf(coef * rec.uv.y);
+			else sines = cr_sinf(coef * rec.p.x) * cr_sinf(coef * rec.p.y) * cr_sinf(coef * rec.p.z);
+			node = sines < 0.0f ? n.in[0] : n.in[1];
+			continue;                                                                       /* tail call */
+		}
+		case CRS_COLOR_BLACKBODY:                                                           /* blackbody.c:38-42 */
+			return cr_color_for_kelvin(NodeEval<D - 1>::value(sc, n.in[0], rec));
+		default: return c4make(0.0f, 0.0f, 0.0f, 1.0f);
+		}
+	}
+}
+template <int D>
+__device__ __noinline__ float NodeEval<D>::value(const DevScene &sc, int node, const Rec &rec) {
+	const crs_node &n = sc.nodes[node];
+	switch (n.kind) {
+	case CRS_VALUE_CONSTANT: return n.f[0];
+	case CRS_VALUE_GRAYSCALE: return cr_grayscale(NodeEval<D>::color(sc, n.in[0], rec));    /* grayscale.c:40-43 */
+	case CRS_VALUE_ALPHA: return NodeEval<D>::alpha(sc, n.in[0], rec);                      /* alpha.c:38-41 */
+	default: return 0.0f;
+	}
+}
+/* .alpha of a color node without evaluating the rgb lanes when the node kind allows it */
+template <int D>
+__device__ __noinline__ float NodeEval<D>::alpha(const DevScene &sc, int node, const Rec &rec) {
+	const crs_node &n = sc.nodes[node];
+	switch (n.kind) {
+	case CRS_COLOR_CONSTANT: return n.f[3];
+	case CRS_COLOR_IMAGE: return cr_image_alpha(sc, n, rec);
+	case CRS_COLOR_BLACKBODY: return 0.0f;
+	default: return NodeEval<D>::color(sc, node, rec).a;
+	}
+}
+template <> struct NodeEval<0> {   /* leaves only */
+	static __device__ __noinline__ col4 color(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_COLOR_CONSTANT: return c4make(n.f[0], n.f[1], n.f[2], n.f[3]);
+		case CRS_COLOR_IMAGE: return cr_image_color(sc, n, rec);
+		case CRS_COLOR_GRADIENT: return cr_gradient(n, rec);
+		default: return c4make(0.0f, 0.0f, 0.0f, 1.0f);
+		}
+	}
+	static __device__ __noinline__ float value(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_VALUE_CONSTANT: return n.f[0];
+		case CRS_VALUE_GRAYSCALE: return cr_grayscale(color(sc, n.in[0], rec));
+		case CRS_VALUE_ALPHA: return alpha(sc, n.in[0], rec);
+		default: return 0.0f;
+		}
+	}
+	static __device__ __noinline__ float alpha(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_COLOR_CONSTANT: return n.f[3];
+		case CRS_COLOR_IMAGE: return cr_image_alpha(sc, n, rec);
+		default: return color(sc, node, rec).a;
+		}
+	}
+};
+typedef NodeEval<CRG_NODE_DEPTH> Nodes;
+
+/* ---- vector.h:252-272 --------------------------------------------------------------------------------------------------- */
+CRD bool cr_refract(v3 in, v3 normal, float niOverNt, v3 &refracted) {
+	const v3 uv = v3norm(in);
+	const float dt = v3dot(uv, normal);
+	const float disc = 1.0f - niOverNt * niOverNt * (1.0f - dt * dt);
+	if (disc > 0.0f) {
+		const v3 A = v3scale(normal, dt);
+		const v3 B = v3sub(uv, A);
+		const v3 C = v3scale(B, niOverNt);
+		const v3 D = v3scale(normal, cr_sqrtf(disc));
+		refracted = v3sub(C, D);
+		return true;
+	}
+	return false;
+}
+CRD float cr_schlick(float cosine, float IOR) {
+	float r0 = cr_div(1.0f - IOR, 1.0f + IOR);
+	r0 = r0 * r0;
+	return r0 + (1.0f - r0) * cr_powf(1.0f - cosine, 5.0f);
+}
+/* shared by glass.c:53-67 and plastic.c:60-74 */
+CRD float cr_fresnel_probability(const Rec &rec, float IOR, v3 &refracted) {
+	v3 outward;
+	float niOverNt, cosine;
+	const float dn = v3dot(rec.inc_d, rec.n);
+	if (dn > 0.0f) {
+		outward = v3neg(rec.n);
+		niOverNt = IOR;
+		cosine = cr_div(IOR * dn, v3len(rec.inc_d));
+	} else {
+		outward = rec.n;
+		niOverNt = cr_div(1.0f, IOR);
+		cosine = -cr_div(dn, v3len(rec.inc_d));
+	}
+	if (cr_refract(rec.inc_d, outward, niOverNt, refracted)) return cr_schlick(cosine, IOR);
+	return 1.0f;
+}
+
+/* one non-composite bsdf node; returns false when `node` is MIX/PLASTIC(diffuse branch)/ADD and sets next */
+CRD BsdfSample cr_sample_leaf(const DevScene &sc, const crs_node &n, uint64_t &rng, const Rec &rec) {
+	BsdfSample s;
+	switch (n.kind) {
+	case CRS_BSDF_DIFFUSE:                                                                  /* diffuse.c:40-47 */
+		s.out = v3norm(v3add(rec.n, cr_random_on_unit_sphere(rng)));
+		s.color = Nodes::color(sc, n.in[0], rec);
+		return s;
+	case CRS_BSDF_ISOTROPIC:                                                                /* isotropic.c:40-47 */
+		s.out = v3norm(cr_random_on_unit_sphere(rng));
+		s.color = Nodes::color(sc, n.in[0], rec);
+		return s;
+	case CRS_BSDF_EMISSIVE: {                                                               /* emission.c:42-49 */
+		s.out = v3norm(v3add(rec.n, cr_random_on_unit_sphere(rng)));
+		const float strength = Nodes::value(sc, n.in[1], rec);
+		s.color = c4coef(strength, Nodes::color(sc, n.in[0], rec));
+		return s;
+	}
+	case CRS_BSDF_METAL: {                                                                  /* metal.c:40-55 */
+		const v3 nd = v3norm(rec.inc_d);
+		v3 reflected = v3reflect(nd, rec.n);
+		const float rough = Nodes::value(sc, n.in[1], rec);
+		if (rough > 0.0f) reflected = v3add(reflected, v3scale(cr_random_on_unit_sphere(rng), rough));
+		s.out = reflected;
+		s.color = Nodes::color(sc, n.in[0], rec);
+		return s;
+	}
+	case CRS_BSDF_GLASS: {                                                                  /* glass.c:41-87 */
+		v3 refracted = v3make(0.0f, 0.0f, 0.0f);
+		v3 reflected = v3reflect(rec.inc_d, rec.n);
+		const float IOR = Nodes::value(sc, n.in[2], rec);
+		const float prob = cr_fresnel_probability(rec, IOR, refracted);
+		const float rough = Nodes::value(sc, n.in[1], rec);
+		if (rough > 0.0f) {
+			const v3 fuzz = v3scale(cr_random_on_unit_sphere(rng), rough);
+			reflected = v3add(reflected, fuzz);
+			refracted = v3add(refracted, fuzz);
+		}
+		s.out = cr_draw(rng) < prob ? reflected : refracted;
+		s.color = Nodes::color(sc, n.in[0], rec);
+		return s;
+	}
+	case CRS_BSDF_TRANSPARENT:                                                              /* transparent.c:40-44 */
+		s.out = rec.inc_d;
+		s.color = Nodes::color(sc, n.in[0], rec);
+		return s;
+	default:
+		s.out = v3make(0.0f, 0.0f, 0.0f);
+		s.color = c4make(0.0f, 0.0f, 0.0f, 1.0f);
+		return s;
+	}
+}
+
+/* material.bsdf->sample(...) — pathtrace.c:46.  Explicit-stack evaluation of the bsdf tree: MIX and
+ * PLASTIC→diffuse are tail calls; ADD pushes "combine" + B and continues with A, so A's draws come
+ * before B's exactly as add.c:44-45. */
+#define CRG_COMBINE (-2)
+CRD BsdfSample cr_sample_bsdf(const DevScene &sc, int root, uint64_t &rng, const Rec &rec) {
+	int todo[CRG_ADD_STACK];
+	BsdfSample vals[CRG_ADD_STACK / 2 + 1];
+	int nt = 0, nv = 0;
+	int node = root;
+	while (true) {
+		BsdfSample s;
+		bool have = false;
+		while (!have) {
+			const crs_node &n = sc.nodes[node];
+			if (n.kind == CRS_BSDF_MIX) {                                                   /* mix.c:42-50 */
+				const float lerp = Nodes::value(sc, n.in[2], rec);
+				node = (cr_draw(rng) > lerp) ? n.in[0] : n.in[1];
+			} else if (n.kind == CRS_BSDF_PLASTIC) {                                        /* plastic.c:42-87 */
+				v3 refracted;
+				const float prob = cr_fresnel_probability(rec, rec.IOR, refracted);
+				if (cr_draw(rng) < prob) {                                                  /* sampleShiny :42-56 */
+					v3 reflected = v3reflect(rec.inc_d, rec.n);
+					const float rough = Nodes::color(sc, n.in[1], rec).r;
+					if (rough > 0.0f) reflected = v3add(reflected, v3scale(cr_random_on_unit_sphere(rng), rough));
+					s.out = reflected;
+					s.color = c4make(1.0f, 1.0f, 1.0f, 1.0f);
+					have = true;
+				} else {
+					node = n.in[2];
+				}
+			} else if (n.kind == CRS_BSDF_ADD && nt + 2 <= CRG_ADD_STACK) {                 /* add.c:42-49 */
+				todo[nt++] = CRG_COMBINE;
+				todo[nt++] = n.in[1];
+				node = n.in[0];
+			} else {
+				s = cr_sample_leaf(sc, n, rng, rec);    /* (an over-deep ADD falls to the black default; rejected at upload) */
+				have = true;
+			}
+		}
+		if (nt == 0) return s;                          /* common case: no ADD in the graph */
+		vals[nv++] = s;
+		while (nt > 0 && todo[nt - 1] == CRG_COMBINE) {
+			--nt;
+			const BsdfSample b = vals[--nv];
+			const BsdfSample a = vals[--nv];
+			BsdfSample r;
+			r.out = v3add(a.out, b.out);
+			r.color = c4add(a.color, b.color);
+			vals[nv++] = r;
+		}
+		if (nt == 0) return vals[0];
+		node = todo[--nt];
+	}
+}
+
+/* scene->background->sample(...) — background.c:39-66 (pathtrace.c:40) */
+static __device__ __noinline__ col4 cr_sample_background(const DevScene &sc, v3 dir) {
+	const crs_node &n = sc.nodes[sc.background];
+	Rec rec;
+	rec.inc_d = dir;
+	rec.p = v3make(0.0f, 0.0f, 0.0f);
+	rec.n = v3make(0.0f, 0.0f, 0.0f);
+	rec.uv.x = 0.0f; rec.uv.y = 0.0f;
+	rec.IOR = 0.0f;
+	const v3 ud = v3norm(dir);
+	const float phi = cr_div(cr_atan2f(ud.z, ud.x), 4.0f) + Nodes::value(sc, n.in[2], rec);
+	const float theta = cr_acosf(cr_div(-ud.y, 1.0f));
+	float u = cr_div(theta, CR_PI);
+	float v = cr_div(phi, CR_PI / 2.0f);
+	u = cr_wrapMinMax(u, 0.0f, 1.0f);
+	v = cr_wrapMinMax(v, 0.0f, 1.0f);
+	rec.uv.x = v; rec.uv.y = u;
+	const float strength = Nodes::value(sc, n.in[1], rec);
+	return c4coef(strength, Nodes::color(sc, n.in[0], rec));
+}
+
+/* ---- hit reconstruction: everything intersectSphere/intersectMesh do after the closest primitive is known ------------------ */
+CRD void cr_texmap_sphere(v3 ud, v2 &uv) {                                                  /* instance.c:33-43 */
+	const float phi = cr_atan2f(ud.z, ud.x);
+	const float theta = cr_asinf(ud.y);
+	float v = cr_div(theta + CR_PI / 2.0f, CR_PI);
+	float u = 1.0f - cr_div(phi + CR_PI, CR_PI * 2.0f);
+	u = cr_wrapMinMax(u, 0.0f, 1.0f);
+	v = cr_wrapMinMax(v, 0.0f, 1.0f);
+	uv.x = u; uv.y = v;
+}
+
+/* fills rec (hitPoint, surfaceNormal, uv, IOR) and returns the global material index */
+CRD int cr_reconstruct_hit(const DevScene &sc, v3 o, v3 d, const Hit &hit, Rec &rec, bool force_uv) {
+	const DevInstance *inst = sc.instances + hit.inst;
+	const float4 *m4 = reinterpret_cast<const float4 *>(inst->Ainv);
+	float Ainv[12], A[12];
+	{
+		const float4 r0 = __ldg(m4 + 0), r1 = __ldg(m4 + 1), r2 = __ldg(m4 + 2);
+		const float4 a0 = __ldg(m4 + 3), a1 = __ldg(m4 + 4), a2 = __ldg(m4 + 5);
+		Ainv[0] = r0.x; Ainv[1] = r0.y; Ainv[2] = r0.z; Ainv[3] = r0.w; Ainv[4] = r1.x; Ainv[5] = r1.y; Ainv[6] = r1.z; Ainv[7] = r1.w;
+		Ainv[8] = r2.x; Ainv[9] = r2.y; Ainv[10] = r2.z; Ainv[11] = r2.w;
+		A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
+		A[8] = a2.x; A[9] = a2.y; A[10] = a2.z; A[11] = a2.w;
+	}
+	const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(&inst->kind));
+	v3 oo, od;
+	cr_object_ray(Ainv, __uint_as_float(meta.z), o, d, oo, od);
+	const v3 p_obj = v3add(oo, v3scale(od, hit.t));                                         /* alongRay(copy, t) */
+	rec.inc_d = d;
+	int material;
+	if (meta.x == CRS_INST_MESH) {
+		const uint32_t poly = __ldg(sc.slot_poly + hit.prim);
+		const float4 *s4 = reinterpret_cast<const float4 *>(sc.spolys + poly);
+		const float4 a = __ldg(s4 + 0), b = __ldg(s4 + 1), c = __ldg(s4 + 2), e = __ldg(s4 + 3);
+		const uint4 f = __ldg(reinterpret_cast<const uint4 *>(s4 + 4));
+		/* a=(n0.xyz,n1.x) b=(n1.yz,n2.xy) c=(n2.z,t0.xy,t1.x) e=(t1.y,t2.xy,material) f=(flags,...) */
+		const float u = hit.u, v = hit.v;
+		const float w = 1.0f - u - v;
+		const uint32_t flags = f.x;
+		v3 nrm;
+		if (flags & 1u) {                                                                   /* poly.c:39-44 */
+			const v3 up = v3scale(v3make(a.w, b.x, b.y), u);
+			const v3 vp = v3scale(v3make(b.z, b.w, c.x), v);
+			const v3 wp = v3scale(v3make(a.x, a.y, a.z), w);
+			nrm = v3add(v3add(up, vp), wp);
+		} else {
+			nrm = v3make(a.x, a.y, a.z);                                                    /* n = e1 x e2 */
+		}
+		if (flags & 2u) {                                                                   /* instance.c:150-167 */
+			const float ucx = c.w * u, ucy = e.x * u;        /* t1 * u */
+			const float vcx = e.y * v, vcy = e.z * v;        /* t2 * v */
+			const float wcx = c.y * w, wcy = c.z * w;        /* t0 * w */
+			rec.uv.x = (ucx + vcx) + wcx;
+			rec.uv.y = (ucy + vcy) + wcy;
+		} else {
+			rec.uv.x = -1.0f; rec.uv.y = -1.0f;
+		}
+		material = (int)__float_as_uint(e.w);
+		rec.p = xf_point(A, p_obj);
+		rec.n = v3norm(xf_vector_transpose(Ainv, nrm));                                     /* instance.c:179-181 */
+	} else {
+		const v3 nobj = v3norm(p_obj);                                                      /* sphere.c:56 */
+		material = (int)__ldg(&inst->material);
+		if (force_uv || (sc.materials[material].flags & 1u)) cr_texmap_sphere(nobj, rec.uv);
+		else { rec.uv.x = 0.0f; rec.uv.y = 0.0f; }   /* uv is dead: no node of this material's graph reads it */
+		rec.p = xf_point(A, p_obj);
+		rec.n = xf_vector_transpose(Ainv, nobj);                                            /* not renormalised, instance.c:56 */
+	}
+	rec.IOR = sc.materials[material].IOR;
+	return material;
+}

@@ -104,3 +104,23 @@ void crscene_free(struct crs_scene *s) {
 	if (s && s->owner) free(s->owner);
 	if (s) memset(s, 0, sizeof(*s));
 }
+
+/* Re-target a loaded scene to another image size / sample count / bounce limit, exactly as the
+ * reference's CLI overrides do (-d WxH, -s N: src/utils/args.c:108-131 applied in
+ * sceneloader.c:425-467) followed by newCamera (src/datatypes/camera.c:22-42): only the aspect-derived
+ * sensor height changes; sensor width, aperture and the composite transform do not depend on W/H.
+ * Values <= 0 keep the current setting. */
+int crscene_set_config(struct crs_scene *s, int width, int height, int samples, int bounces) {
+	if (!s) return -1;
+	if (width > 0 && height > 0) {
+		s->prefs.image_width = (uint32_t)width;
+		s->prefs.image_height = (uint32_t)height;
+		s->camera.width = width;
+		s->camera.height = height;
+		const float aspect = (float)s->camera.width / (float)s->camera.height; /* camera.c:29 */
+		s->camera.sensor_y = s->camera.sensor_x / aspect;                       /* camera.c:31 */
+	}
+	if (samples > 0) s->prefs.sample_count = (uint32_t)samples;
+	if (bounces > 0) s->prefs.bounces = (uint32_t)bounces;
+	return 0;
+}

@@ -1,0 +1,98 @@
+/*
+ * crgpu.h — C ABI of the B200 path-trace hot loop (libcrgpu.so).
+ *
+ * This is the drop-in boundary.  c-ray's tile dispatcher (`renderFrame`, reference
+ * src/renderer/renderer.c:40-180) starts worker threads through a `struct crThread` slot whose
+ * `threadFunc` is today `renderThread` (renderer.c:258-327) or `networkRenderThread`
+ * (src/utils/protocol/server.c:215-263).  A GPU worker thread occupies the same slot
+ * (c-ray_b200/host/gpu_render_thread.c, binding shown in INTEGRATION.md) and calls ONLY the functions
+ * below — plain pointers and sizes, no CUDA or torch types.
+ *
+ *   reference interface replaced                                  entry point here
+ *   -----------------------------------------------------------   ---------------------------------
+ *   (none; scene is read through pointers, scene.h:14-39)          crgpu_scene_create / _destroy
+ *   renderThread inner loops, renderer.c:271-320                   crgpu_render_tile
+ *     initSampler  sampler.c:41-44   getCameraRay camera.c:58-87
+ *     pathTrace    pathtrace.c:32-60 traverseTopLevelBvh bvh.c:488
+ *     bsdf->sample nodes/shaders     running average renderer.c:288-294
+ *   colorToSRGB + setPixel(image), renderer.c:297-300              crgpu_framebuffer_to_srgb8
+ *   textureGetPixel(renderBuffer), renderer.c:283                  crgpu_framebuffer_read / _write / _clear
+ *   tile gather of the cluster mode, server.c:159-174              crgpu_framebuffer_device_ptr (+ NCCL in the host)
+ *
+ * All functions return 0 on success or a negative CRGPU_ERR_* code; crgpu_last_error() gives text.
+ * The host turns errors into logr(warning|error, ...) like the rest of c-ray (logging.c:50-74).
+ * There is NO CPU fallback: without a CUDA device every call fails with CRGPU_ERR_NO_DEVICE.
+ */
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include "crscene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRGPU_OK                 0
+#define CRGPU_ERR_NO_DEVICE     -1
+#define CRGPU_ERR_CUDA          -2
+#define CRGPU_ERR_BAD_ARGUMENT  -3
+#define CRGPU_ERR_UNSUPPORTED   -4   /* node graph deeper than the device interpreter supports, etc. */
+#define CRGPU_ERR_NOMEM         -5
+
+typedef struct crgpu_scene crgpu_scene;
+
+/* Per-call statistics (all counted on the device). */
+struct crgpu_stats {
+	uint64_t paths;          /* pixel-passes started (one pathTrace call each) */
+	uint64_t rays;           /* closest-hit queries, one per getClosestIsect (pathtrace.c:38) */
+	uint64_t node_pairs;     /* P: BVH child-pair steps, both levels   (only with CRGPU_FLAG_COUNT) */
+	uint64_t tri_tests;      /* T: triangle tests                      (only with CRGPU_FLAG_COUNT) */
+	uint64_t sphere_tests;   /* S: sphere tests                        (only with CRGPU_FLAG_COUNT) */
+	uint64_t inst_visits;    /* I: mesh-instance visits                (only with CRGPU_FLAG_COUNT) */
+	uint64_t kernel_launches;/* CUDA kernels launched by this call */
+	float    trace_ms;       /* device time inside the BVH-traversal kernel (CUDA events), if CRGPU_FLAG_TIME_KERNELS */
+	float    shade_ms;       /* device time inside the shade kernel, same condition */
+	float    total_ms;       /* device time of the whole call on its stream, same condition */
+	float    pad;
+};
+
+#define CRGPU_FLAG_COUNT         0x1u  /* run the instrumented traversal kernel (slower; fills P/T/S/I) */
+#define CRGPU_FLAG_TIME_KERNELS  0x2u  /* bracket every kernel with CUDA events (adds sync at the end only) */
+
+int crgpu_device_count(int *n);
+const char *crgpu_last_error(void);
+
+/* Upload a flattened scene (include/crscene.h) to `device`.  The device keeps its own replicas; the
+ * flat arrays may be freed after the call.  Also allocates the fp32 framebuffer (W*H*3, row H-1-y:
+ * the layout of state.renderBuffer, scene.c:200 + texture.c:24-28), zero-initialised. */
+int crgpu_scene_create(const struct crs_scene *flat, int device, crgpu_scene **out);
+int crgpu_scene_destroy(crgpu_scene *s);
+
+/* Limit on paths in flight per wavefront batch (default 8M); the tile's passes are processed in
+ * batches of floor(max_paths / tile_pixels) passes.  Results do not depend on it. */
+int crgpu_set_max_paths_in_flight(crgpu_scene *s, uint64_t max_paths);
+
+/* Render passes [pass_begin, pass_begin+pass_count) of the tile [x0,x1) x [y0,y1) (y up, end
+ * exclusive: `struct renderTile`, tile.h:28-37) into the device framebuffer, continuing the running
+ * average stored there.  maxPasses and bounces come from the scene prefs (they seed the sampler,
+ * sampler.c:42).  Synchronous: returns when the device is done.  `stats` may be NULL. */
+int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
+					  int pass_begin, int pass_count, unsigned flags, struct crgpu_stats *stats);
+
+/* Framebuffer access.  Host variants copy rows of the tile rectangle (or the whole frame when
+ * x1<=x0) between the device framebuffer and a host buffer with the SAME W*H*3 layout. */
+int crgpu_framebuffer_clear(crgpu_scene *s);
+int crgpu_framebuffer_read(crgpu_scene *s, float *host_rgb, int x0, int y0, int x1, int y1);
+int crgpu_framebuffer_write(crgpu_scene *s, const float *host_rgb, int x0, int y0, int x1, int y1);
+/* 8-bit sRGB image of the current framebuffer (renderer.c:297-300), W*H*3 bytes, same row order. */
+int crgpu_framebuffer_to_srgb8(crgpu_scene *s, uint8_t *host_rgb8);
+/* Raw device pointer of the fp32 framebuffer (for the NCCL gather done by the multi-GPU host). */
+int crgpu_framebuffer_device_ptr(crgpu_scene *s, void **dev_ptr, size_t *bytes);
+
+/* Known-answer hook used by the parity tests: camera ray → closest hit → bsdf sample for `count`
+ * (x, y, pass) triples, in the 160-byte record layout of oracle/ref_harness.c `struct hit_kat`. */
+int crgpu_trace_kat(crgpu_scene *s, const int32_t *xyp, int count, void *records_out);
+
+#ifdef __cplusplus
+}
+#endif

@@ -58,6 +58,7 @@ def lib():
         L.crscene_load.argtypes = [C.POINTER(Scene), C.c_char_p]
         L.crscene_load.restype = C.c_int
         L.crscene_free.argtypes = [C.POINTER(Scene)]
+        L.crscene_set_config.argtypes = [C.POINTER(Scene)] + [C.c_int] * 4
         L.cro_render.argtypes = [C.POINTER(Scene)] + [C.c_int] * 6 + [C.c_void_p, C.c_int, C.POINTER(Counters)]
         L.cro_render.restype = C.c_int
         L.cro_sampler_kat.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -68,11 +69,12 @@ def lib():
 
 
 class OracleScene:
-    def __init__(self, path):
+    def __init__(self, path, width=0, height=0, samples=0, bounces=0):
         self.s = Scene()
         rc = lib().crscene_load(C.byref(self.s), path.encode())
         if rc != 0:
             raise RuntimeError(f"crscene_load({path}) failed: {rc}")
+        lib().crscene_set_config(C.byref(self.s), width, height, samples, bounces)
         self.W = self.s.prefs.image_width
         self.H = self.s.prefs.image_height
 
