@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""bench.py — Mray/s (and Msample/s) of the B200 path-trace hot loop on BASELINE.json's headline config.
+
+A "step" is one complete render of the workload frame: default = configs[1] of BASELINE.json,
+input/hdr.json at 1920x1080, 1000 spp, 32 bounces (scene flattened by the reference's own loader at build
+time: scenes/_built/hdr.crscene).  Image tiles (the reference's quantizeImage grid) are sharded
+round-robin over the ranks; the frame is fixed, so this is STRONG scaling.  With N>1 the fp32
+framebuffer tiles are gathered on rank 0 over NCCL inside the timed region.
+
+  value      Mray/s, whole job, scene + framebuffer resident in HBM, device-timed (CUDA events), max over ranks
+  e2e        same metric through the public C ABI with HOST buffers: crgpu_scene_create from the host-resident
+             flat scene (H2D of every array) + render + NCCL gather + crgpu_framebuffer_read (D2H), wall clock
+  roofline   K2 (k_trace) algorithmic bytes / its CUDA-event time, vs the measured HBM copy peak
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/cray_ref_stock, pthreads, all host cores) on a bounded
+             sample (same frame, fewer spp) — a reported baseline, not the optimisation target
+
+`--impl reference` times that same reference binary as its own arm.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "c-ray_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {   # BASELINE.json configs[1..3]
+    "hdr": dict(scene="hdr", width=1920, height=1080, spp=1000, bounces=32),
+    "refraction": dict(scene="refraction", width=1920, height=1080, spp=2500, bounces=512),
+    "venus": dict(scene="venus", width=2560, height=1600, spp=1000, bounces=25),
+    "scene": dict(scene="scene", width=320, height=200, spp=16, bounces=4),
+}
+PEAK_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hdr", choices=sorted(WORKLOADS))
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--bounces", type=int, default=0)
+    ap.add_argument("--tile", type=int, default=0, help="tile edge for sharding (0 = auto)")
+    ap.add_argument("--max-paths", type=int, default=0, help="paths in flight per wavefront batch (0 = library default)")
+    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    w = dict(WORKLOADS[args.workload])
+    for k, a in (("width", args.width), ("height", args.height), ("spp", args.spp), ("bounces", args.bounces)):
+        if a > 0:
+            w[k] = a
+    return w
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return PEAK_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][2]) if self.samples[0][2].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def tiles_of(W, H, t):
+    return [(x, y, min(x + t, W), min(y + t, H)) for y in range(0, H, t) for x in range(0, W, t)]
+
+
+def run_reference(scene, W, H, spp, bounces, threads):
+    """The unmodified reference (stock flags, pthreads) on the host cores; returns (seconds of renderFrame, samples)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "cray_ref_stock")
+    js = os.path.join(ROOT, "oracle", "_ref", "input", scene + ".json")
+    if not (os.path.exists(exe) and os.path.exists(js)):
+        return None
+    out = f"/tmp/cray_ref_bench_{os.getpid()}.f32"
+    r = subprocess.run([exe, "render", js, str(W), str(H), str(spp), str(bounces), str(threads), "0", "0", out],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        os.remove(out)
+    except OSError:
+        pass
+    m = re.search(r"REF_RENDER .*threads=(\d+) seconds=([0-9.]+)", r.stdout)
+    if r.returncode != 0 or not m:
+        return None
+    return float(m.group(2)), W * H * spp, int(m.group(1))
+
+
+def reference_arm(args, w, rank):
+    """bench.py --impl reference: the reference's own CPU implementation of the path, rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    spp = args.cpu_spp or max(1, min(w["spp"], int(2.0e6 * cores * 1.0 / (w["width"] * w["height"])) or 1))  # ~1 s/step/core-rate guess
+    rays_per_sample = float(os.environ.get("CRAY_RAYS_PER_SAMPLE", "0")) or None
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = run_reference(w["scene"], w["width"], w["height"], spp, w["bounces"], cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cray_ref_stock or its input assets are missing (run build() in the build container)"}))
+            return
+        if i >= args.warmup:
+            times.append(r[0])
+        threads = r[2]
+    total_s = sum(times)
+    samples = w["width"] * w["height"] * spp * args.steps
+    msample = samples / total_s / 1e6
+    # the reference never counts rays; rays/sample of the same scene+bounces is measured by the oracle port
+    rps = rays_per_sample or oracle_rays_per_sample(w, spp)
+    value = msample * rps
+    line = {"metric": "Mray/s", "value": round(value, 3), "unit": "Mray/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1e3 * total_s / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "bundled scene input/%s.json (reference assets copied at build time)" % w["scene"], "impl": "reference",
+            "config": {"workload": f"input/{w['scene']}.json {w['width']}x{w['height']} {w['spp']} spp {w['bounces']} bounces", "spp_per_step": spp,
+                       "note": "bounded sample: same frame, fewer spp (CPU cost is linear in spp, renderer.c:275)"},
+            "msample_per_s": round(msample, 3), "rays_per_sample": round(rps, 4),
+            "cpu_baseline": {"value": round(value, 3), "unit": "Mray/s", "cores": threads, "kind": "reference",
+                             "sample": f"{w['width']}x{w['height']} x {spp} spp per step, pthreads -j {threads}, stock flags (-O2 -ftree-vectorize -march=x86-64-v3)"},
+            "e2e": {"value": round(value, 3), "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def oracle_rays_per_sample(w, spp):
+    """rays per pathTrace call for this scene/bounce limit, counted by the CPU oracle on a small frame."""
+    import oracle_lib as O
+    sw, sh = max(16, w["width"] // 8), max(16, w["height"] // 8)
+    o = O.OracleScene(os.path.join(ROOT, "scenes", "_built", w["scene"] + ".crscene"), sw, sh, max(1, min(spp, 4)), w["bounces"])
+    _, c = o.render(threads=os.cpu_count() or 1, count=True)
+    o.close()
+    return c["rays"] / c["paths"]
+
+
+def main():
+    args = parse_args()
+    w = workload(args)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, w, rank)
+        return
+
+    import numpy as np
+    import torch
+    import crgpu
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    W, H, spp, bounces = w["width"], w["height"], w["spp"], w["bounces"]
+    scene_path = os.path.join(ROOT, "scenes", "_built", w["scene"] + ".crscene")
+    if not os.path.exists(scene_path):
+        raise SystemExit(f"{scene_path} missing: run __graft_entry__.build() in the build container")
+    tile = args.tile or (64 if world > 1 else 0)
+    g = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
+    rects = tiles_of(W, H, tile)[rank::world] if tile else [(0, 0, W, H)]
+
+    # zero-copy torch view of the device framebuffer (for the NCCL gather)
+    ptr, nbytes = g.device_ptr()
+
+    class _Fb:
+        __cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    fb = torch.as_tensor(_Fb(), device=dev)
+
+    def pack():
+        return torch.cat([fb[H - y1:H - y0, x0:x1].reshape(-1) for (x0, y0, x1, y1) in rects])
+
+    all_rects = [tiles_of(W, H, tile)[r::world] for r in range(world)] if world > 1 else None
+    sizes = [sum((x1 - x0) * (y1 - y0) * 3 for (x0, y0, x1, y1) in rs) for rs in all_rects] if world > 1 else None
+
+    def gather_to_rank0():
+        if world == 1:
+            return
+        mine = pack()
+        pad = max(sizes)
+        buf = torch.zeros(pad, device=dev, dtype=torch.float32)
+        buf[:mine.numel()] = mine
+        outs = [torch.empty(pad, device=dev, dtype=torch.float32) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, outs, dst=0)
+        if rank == 0:
+            for r in range(1, world):
+                off = 0
+                for (x0, y0, x1, y1) in all_rects[r]:
+                    n = (x1 - x0) * (y1 - y0) * 3
+                    fb[H - y1:H - y0, x0:x1] = outs[r][off:off + n].view(y1 - y0, x1 - x0, 3)
+                    off += n
+
+    def step(flags=0):
+        """one complete frame: enqueue everything on torch's current stream, no host sync inside"""
+        g.clear()
+        for r in rects:
+            g.render_tile(*r, flags=flags | crgpu.FLAG_ASYNC)
+        gather_to_rank0()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    g.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    for _ in range(args.warmup):
+        step()
+    g.get_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the library enqueues on torch's current stream (crgpu_set_stream), so these events bracket exactly its kernels
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    stats = g.get_stats()
+    clocks = sampler.summary()
+    tms = torch.tensor([ms, float(stats["rays"]), float(stats["paths"]), float(stats["kernel_launches"])], device=dev, dtype=torch.float64)
+    if dist:
+        mx = tms.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tms.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, rays, paths, launches = float(mx[0]), float(sm[1]), float(sm[2]), float(sm[3])
+    else:
+        ms, rays, paths, launches = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3])
+    value = rays / ms / 1e3                      # Mray/s, whole job
+    msample = paths / ms / 1e3
+
+    # ---- e2e through the C ABI with host buffers (scene upload + render + gather + read back) ---------------
+    g.close()
+    host_fb = np.empty((H, W, 3), dtype=np.float32)
+    h2d = os.path.getsize(scene_path)
+    barrier()
+    t0 = time.perf_counter()
+    e_rays = 0
+    e_steps = max(1, min(args.steps, 2))
+    for _ in range(e_steps):
+        g2 = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
+        ptr, _ = g2.device_ptr()
+
+        class _Fb2:
+            __cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        fb = torch.as_tensor(_Fb2(), device=dev)
+        g = g2
+        g.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        step()
+        e_rays += g.get_stats()["rays"]
+        if rank == 0:
+            g2.read(host_fb)
+        if _ != e_steps - 1:
+            g2.close()
+    barrier()
+    e_ms = 1e3 * (time.perf_counter() - t0)
+    et = torch.tensor([e_ms, float(e_rays)], device=dev, dtype=torch.float64)
+    if dist:
+        a = et.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = et.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e_ms, e_rays = float(a[0]), float(b[1])
+    e2e_value = e_rays / e_ms / 1e3
+
+    # ---- roofline of K2: one profiled step (per-kernel CUDA events) + one counted step (P/T/S/I) ---------------
+    step(flags=crgpu.FLAG_TIME_KERNELS)
+    prof = g.get_stats()
+    cspp = min(spp, 8)
+    gc = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
+    cnt = None
+    for r in rects:
+        s_ = gc.render_tile(*r, pass_begin=0, pass_count=cspp, flags=crgpu.FLAG_COUNT)
+        cnt = s_ if cnt is None else {k: cnt[k] + s_[k] for k in cnt}
+    gc.close()
+    P, T, S, I = (cnt[k] / cnt["rays"] for k in ("node_pairs", "tri_tests", "sphere_tests", "inst_visits"))
+    b_ray = 64 * P + 80 * T + 128 * I + 16 * S + 72
+    peak, peak_kind = peaks()
+    trace_s = prof["trace_ms"] / 1e3
+    achieved = (prof["rays"] * b_ray / trace_s / 1e9) if trace_s > 0 else None
+    roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 2) if achieved else None, "peak": peak,
+                "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": None,
+                "bytes_per_ray": round(b_ray, 1), "per_ray": {"P": round(P, 3), "T": round(T, 3), "I": round(I, 3), "S": round(S, 3)},
+                "trace_share_of_step": round(prof["trace_ms"] / prof["total_ms"], 4) if prof["total_ms"] else None,
+                "shade_share_of_step": round(prof["shade_ms"] / prof["total_ms"], 4) if prof["total_ms"] else None,
+                "trace_gray_per_s": round(prof["rays"] / trace_s / 1e9, 3) if trace_s > 0 else None,
+                "note": "achieved = rays * B_ray / sum of k_trace launch durations (CUDA events, rank-local profiled step); "
+                        "the scene (~50 MB) is L2-resident, so DRAM traffic is mostly the wavefront state"}
+    g.close()
+
+    # ---- CPU baseline: the unmodified reference on the host cores, bounded sample, rank 0 at N=1 ------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cspp = args.cpu_spp or max(1, min(spp, int(8.0e6 * cores * 1.0 / (W * H)) or 1))   # ~10-20 s at ~0.6 Msample/s/core
+        r = run_reference(w["scene"], W, H, cspp, bounces, cores)
+        if r:
+            secs, samples, threads = r
+            cpu = {"value": round(samples / secs / 1e6 * (rays / paths), 3), "unit": "Mray/s", "cores": threads, "kind": "reference",
+                   "msample_per_s": round(samples / secs / 1e6, 3), "seconds": round(secs, 2),
+                   "sample": f"unmodified reference (oracle/_ref/cray_ref_stock, pthreads -j {threads}) on input/{w['scene']}.json {W}x{H}, "
+                             f"{cspp} spp of {spp}, {bounces} bounces; Mray/s = its Msample/s x {rays / paths:.3f} rays/sample counted on the GPU run"}
+        else:
+            cpu = {"value": None, "unit": "Mray/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
+
+    if rank == 0:
+        line = {"metric": "Mray/s", "value": round(value, 2), "unit": "Mray/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "bundled scene input/%s.json flattened by the reference loader at build time (no synthetic tensors on this path)" % w["scene"],
+                "config": {"workload": f"input/{w['scene']}.json {W}x{H} {spp} spp {bounces} bounces", "tile": tile or "whole frame",
+                           "parallelism": f"tile-sharded x{world}" if world > 1 else "1 GPU",
+                           "l2": "wavefront state (GBs per step) streams through the 126 MB L2: inputs larger than L2, no explicit flush"},
+                "msample_per_s": round(msample, 2), "rays_per_sample": round(rays / paths, 4),
+                "e2e": {"value": round(e2e_value, 2), "unit": "Mray/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * W * 3 * 4,
+                        "ms_per_step": round(e_ms / e_steps, 3), "steps": e_steps,
+                        "what": "crscene (host) -> crgpu_scene_create -> crgpu_render_tile xtiles -> NCCL gather -> crgpu_framebuffer_read (host)"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libcrgpu.so")
 
 FLAG_COUNT = 0x1
 FLAG_TIME_KERNELS = 0x2
+FLAG_ASYNC = 0x4
 
 
 class Prefs(C.Structure):
@@ -68,6 +69,8 @@ def lib():
         L.crgpu_scene_destroy.argtypes = [P]
         L.crgpu_set_max_paths_in_flight.argtypes = [P, C.c_uint64]
         L.crgpu_render_tile.argtypes = [P] + [C.c_int] * 6 + [C.c_uint, C.POINTER(Stats)]
+        L.crgpu_set_stream.argtypes = [P, P]
+        L.crgpu_get_stats.argtypes = [P, C.POINTER(Stats)]
         L.crgpu_framebuffer_clear.argtypes = [P]
         L.crgpu_framebuffer_read.argtypes = [P, P] + [C.c_int] * 4
         L.crgpu_framebuffer_write.argtypes = [P, P] + [C.c_int] * 4
@@ -78,7 +81,7 @@ def lib():
         L.crscene_free.argtypes = [C.POINTER(FlatScene)]
         L.crscene_set_config.argtypes = [C.POINTER(FlatScene)] + [C.c_int] * 4
         for f in ("crgpu_device_count", "crgpu_scene_create", "crgpu_scene_destroy", "crgpu_set_max_paths_in_flight",
-                  "crgpu_render_tile", "crgpu_framebuffer_clear", "crgpu_framebuffer_read", "crgpu_framebuffer_write",
+                  "crgpu_render_tile", "crgpu_set_stream", "crgpu_get_stats", "crgpu_framebuffer_clear", "crgpu_framebuffer_read", "crgpu_framebuffer_write",
                   "crgpu_framebuffer_to_srgb8", "crgpu_framebuffer_device_ptr", "crgpu_trace_kat", "crscene_load",
                   "crscene_set_config"):
             getattr(L, f).restype = C.c_int
@@ -127,6 +130,15 @@ class GpuScene:
             pass_count = self.samples - pass_begin
         _check(lib().crgpu_render_tile(self.handle, x0, y0, x1, y1, pass_begin, pass_count, flags, C.byref(st)),
                "crgpu_render_tile")
+        return None if (flags & FLAG_ASYNC) else st.as_dict()
+
+    def set_stream(self, cuda_stream_ptr):
+        """Enqueue on a caller-owned cudaStream_t (int pointer, e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(lib().crgpu_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)), "crgpu_set_stream")
+
+    def get_stats(self):
+        st = Stats()
+        _check(lib().crgpu_get_stats(self.handle, C.byref(st)), "crgpu_get_stats")
         return st.as_dict()
 
     def render_frame(self, flags=0, tile=None):

@@ -43,7 +43,11 @@ extern "C" int crgpu_device_count(int *n) {
 struct crgpu_scene {
 	int device;
 	int sm_count;
-	cudaStream_t stream;
+	cudaStream_t stream;       /* the stream work is enqueued on (own_stream unless crgpu_set_stream) */
+	cudaStream_t own_stream;
+	unsigned long long fetched[8];   /* device counters at the previous stats fetch */
+	uint64_t pend_paths, pend_launches;
+	float pend_trace_ms, pend_shade_ms, pend_total_ms;
 	DevScene dev;
 	DevScene *dev_copy;        /* the same descriptor in HBM, for kernels that call noinline device functions */
 	std::vector<void *> allocs;
@@ -219,12 +223,13 @@ extern "C" int crgpu_scene_destroy(crgpu_scene *s) {
 	if (!s) return CRGPU_OK;
 	cudaSetDevice(s->device);
 	if (s->stream) cudaStreamSynchronize(s->stream);
+	if (s->own_stream && s->own_stream != s->stream) cudaStreamSynchronize(s->own_stream);
 	for (void *p : s->allocs) cudaFree(p);
 	WaveBuffers &w = s->wb;
 	void *ptrs[] = { w.stA[0], w.stA[1], w.stB[0], w.stB[1], w.stC[0], w.stC[1], w.hit, w.hitInst, w.L, w.counts, w.stats, s->fb, s->fb8 };
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
-	if (s->stream) cudaStreamDestroy(s->stream);
+	if (s->own_stream) cudaStreamDestroy(s->own_stream);
 	delete s;
 	return CRGPU_OK;
 }
@@ -246,7 +251,9 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	crgpu_scene *s = new crgpu_scene();
 	memset(&s->dev, 0, sizeof s->dev);
 	memset(&s->wb, 0, sizeof s->wb);
-	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->cap_paths = 0;
+	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->own_stream = nullptr; s->cap_paths = 0;
+	memset(s->fetched, 0, sizeof s->fetched);
+	s->pend_paths = s->pend_launches = 0; s->pend_trace_ms = s->pend_shade_ms = s->pend_total_ms = 0.f;
 	s->max_paths = 8ull << 20;
 	for (auto &e : s->ev) e = nullptr;
 #define FAIL_IF(x) do { int rc_ = (x); if (rc_) { crgpu_scene_destroy(s); return rc_; } } while (0)
@@ -254,7 +261,8 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	cudaDeviceProp prop;
 	CUS(cudaGetDeviceProperties(&prop, device));
 	s->sm_count = prop.multiProcessorCount;
-	CUS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	CUS(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+	s->stream = s->own_stream;
 	for (auto &e : s->ev) CUS(cudaEventCreate(&e));
 
 	/* materials + graph validation */
@@ -442,6 +450,7 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	CUS(cudaMemset(s->fb, 0, s->fb_floats * sizeof(float)));
 	CUS(cudaMalloc((void **)&s->wb.counts, 2 * sizeof(unsigned)));
 	CUS(cudaMalloc((void **)&s->wb.stats, 8 * sizeof(unsigned long long)));
+	CUS(cudaMemset(s->wb.stats, 0, 8 * sizeof(unsigned long long)));
 	CUS(cudaDeviceSynchronize());
 #undef FAIL_IF
 #undef CUS
@@ -487,7 +496,6 @@ extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 	const int grid = s->sm_count * 8;
 	uint64_t launches = 0;
 	float trace_ms = 0.f, shade_ms = 0.f;
-	CU(cudaMemsetAsync(s->wb.stats, 0, 8 * sizeof(unsigned long long), st));
 	if (timing) CU(cudaEventRecord(s->ev[0], st));
 	std::vector<cudaEvent_t> tev;   /* per-kernel events when timing */
 	for (int pb = pass_begin; pb < pass_begin + pass_count; pb += (int)batch) {
@@ -510,11 +518,11 @@ extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 	}
 	if (timing) CU(cudaEventRecord(s->ev[1], st));
 	CU(cudaGetLastError());
-	unsigned long long h[8];
-	CU(cudaMemcpyAsync(h, s->wb.stats, sizeof h, cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
-	float total_ms = 0.f;
+	s->pend_paths += tile_pixels * (uint64_t)pass_count;
+	s->pend_launches += launches;
 	if (timing) {
+		CU(cudaStreamSynchronize(st));
+		float total_ms = 0.f;
 		cudaEventElapsedTime(&total_ms, s->ev[0], s->ev[1]);
 		for (size_t i = 0; i + 3 <= tev.size(); i += 3) {
 			float a = 0.f, b = 0.f;
@@ -523,14 +531,36 @@ extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 			trace_ms += a; shade_ms += b;
 		}
 		for (cudaEvent_t e : tev) cudaEventDestroy(e);
+		s->pend_trace_ms += trace_ms; s->pend_shade_ms += shade_ms; s->pend_total_ms += total_ms;
 	}
+	if (flags & CRGPU_FLAG_ASYNC) return CRGPU_OK;
+	return crgpu_get_stats(s, stats);
+}
+
+extern "C" int crgpu_get_stats(crgpu_scene *s, struct crgpu_stats *stats) {
+	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
+	CU(cudaSetDevice(s->device));
+	unsigned long long h[8];
+	CU(cudaMemcpyAsync(h, s->wb.stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+	CU(cudaStreamSynchronize(s->stream));
 	if (stats) {
 		memset(stats, 0, sizeof *stats);
-		stats->paths = tile_pixels * (uint64_t)pass_count;
-		stats->rays = h[0]; stats->node_pairs = h[1]; stats->tri_tests = h[2]; stats->sphere_tests = h[3]; stats->inst_visits = h[4];
-		stats->kernel_launches = launches;
-		stats->trace_ms = trace_ms; stats->shade_ms = shade_ms; stats->total_ms = total_ms;
+		stats->paths = s->pend_paths;
+		stats->rays = h[0] - s->fetched[0]; stats->node_pairs = h[1] - s->fetched[1]; stats->tri_tests = h[2] - s->fetched[2];
+		stats->sphere_tests = h[3] - s->fetched[3]; stats->inst_visits = h[4] - s->fetched[4];
+		stats->kernel_launches = s->pend_launches;
+		stats->trace_ms = s->pend_trace_ms; stats->shade_ms = s->pend_shade_ms; stats->total_ms = s->pend_total_ms;
 	}
+	memcpy(s->fetched, h, sizeof h);
+	s->pend_paths = s->pend_launches = 0; s->pend_trace_ms = s->pend_shade_ms = s->pend_total_ms = 0.f;
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_set_stream(crgpu_scene *s, void *cuda_stream) {
+	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
+	CU(cudaSetDevice(s->device));
+	CU(cudaStreamSynchronize(s->stream));
+	s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->own_stream;
 	return CRGPU_OK;
 }
 

@@ -58,6 +58,7 @@ struct crgpu_stats {
 
 #define CRGPU_FLAG_COUNT         0x1u  /* run the instrumented traversal kernel (slower; fills P/T/S/I) */
 #define CRGPU_FLAG_TIME_KERNELS  0x2u  /* bracket every kernel with CUDA events (adds sync at the end only) */
+#define CRGPU_FLAG_ASYNC         0x4u  /* only enqueue on the scene's stream; fetch the numbers later with crgpu_get_stats */
 
 int crgpu_device_count(int *n);
 const char *crgpu_last_error(void);
@@ -75,9 +76,18 @@ int crgpu_set_max_paths_in_flight(crgpu_scene *s, uint64_t max_paths);
 /* Render passes [pass_begin, pass_begin+pass_count) of the tile [x0,x1) x [y0,y1) (y up, end
  * exclusive: `struct renderTile`, tile.h:28-37) into the device framebuffer, continuing the running
  * average stored there.  maxPasses and bounces come from the scene prefs (they seed the sampler,
- * sampler.c:42).  Synchronous: returns when the device is done.  `stats` may be NULL. */
+ * sampler.c:42).  Synchronous (returns when the device is done, `stats` = this call) unless
+ * CRGPU_FLAG_ASYNC is given.  `stats` may be NULL. */
 int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 					  int pass_begin, int pass_count, unsigned flags, struct crgpu_stats *stats);
+
+/* Run on a caller-owned CUDA stream (a `cudaStream_t` passed as void*; NULL restores the scene's own
+ * stream).  Lets a host that already has a stream (e.g. the one its NCCL collectives use) order the
+ * kernels with its own work and time them with its own events. */
+int crgpu_set_stream(crgpu_scene *s, void *cuda_stream);
+/* Synchronise the stream and return the statistics accumulated since the previous fetch (by
+ * crgpu_get_stats or by a synchronous crgpu_render_tile). */
+int crgpu_get_stats(crgpu_scene *s, struct crgpu_stats *stats);
 
 /* Framebuffer access.  Host variants copy rows of the tile rectangle (or the whole frame when
  * x1<=x0) between the device framebuffer and a host buffer with the SAME W*H*3 layout. */

@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "c-ray_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+BUILT = os.path.join(ROOT, "scenes", "_built")
+GOLDEN_SCENES = ["g_nodes", "g_legacy", "g_single", "g_meshmat"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure the shared libraries exist (cheap no-op when they are already built)."""
+    import __graft_entry__ as g
+    g.build(quiet=True)

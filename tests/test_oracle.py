@@ -1,0 +1,107 @@
+"""CPU tests: the oracle (oracle/cray_oracle.c) against the reference's own outputs.
+
+The golden files were produced by the unmodified reference built with -ffp-contract=off
+(tests/golden/make_golden.py).  The bar for the oracle is BIT-EXACT fp32.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import GOLDEN, GOLDEN_SCENES, BUILT
+
+
+def test_sampler_kat_bit_exact():
+    k = np.fromfile(os.path.join(GOLDEN, "kat.bin"), dtype=np.uint32).reshape(-1, 16)
+    assert len(k) == 10
+    for row in k:
+        pix, p, mp = (int(v) for v in row[:3])
+        mine = O.sampler_kat(pix, p, mp, 13)
+        assert np.array_equal(row[3:], mine.view(np.uint32)), (pix, p, mp)
+
+
+def test_sampler_seed_wraps_in_32_bits():
+    # sampler.c:42: pixelIndex * maxPasses + pass is uint32 arithmetic
+    a = O.sampler_kat(2073599, 2499, 2500, 4)
+    wrapped = (2073599 * 2500 + 2499) & 0xFFFFFFFF
+    b = O.sampler_kat(wrapped, 0, 1, 4)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_draw_range_inclusive_one():
+    # random.c:17: 2^-32 * (float)u32 rounds up to exactly 1.0f for u32 >= 2^32-128
+    v = O.sampler_kat(0, 0, 1, 4096)
+    assert v.min() >= 0.0 and v.max() <= 1.0
+
+
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_framebuffer_bit_exact(name):
+    sc = O.OracleScene(os.path.join(GOLDEN, name + ".crscene"))
+    ref = np.fromfile(os.path.join(GOLDEN, name + ".f32"), dtype=np.float32).reshape(sc.H, sc.W, 3)
+    img = sc.render(threads=4)
+    assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+    sc.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_hit_records_bit_exact(name):
+    sc = O.OracleScene(os.path.join(GOLDEN, name + ".crscene"))
+    h = np.fromfile(os.path.join(GOLDEN, name + ".hits.bin"), dtype=O.HIT_KAT_DTYPE)
+    assert len(h) == 96
+    for i, r in enumerate(h):
+        m = sc.trace_kat(int(r["x"]), int(r["y"]), i % sc.s.prefs.sample_count)
+        assert r.tobytes() == m.tobytes(), (name, i)
+    sc.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_tiles_and_pass_ranges_compose(name):
+    """Tile size, thread count and splitting the passes never change a pixel (renderer.c:271-320)."""
+    sc = O.OracleScene(os.path.join(GOLDEN, name + ".crscene"))
+    ref = np.fromfile(os.path.join(GOLDEN, name + ".f32"), dtype=np.float32).reshape(sc.H, sc.W, 3)
+    img = np.zeros_like(ref)
+    spp = sc.s.prefs.sample_count
+    for (pb, pc) in ((0, 3), (3, spp - 3)):
+        for y0 in range(0, sc.H, 16):
+            for x0 in range(0, sc.W, 16):
+                sc.render(threads=1, tile=(x0, y0, min(x0 + 16, sc.W), min(y0 + 16, sc.H)), passes=(pb, pc), rgb=img)
+    assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+    sc.close()
+
+
+def test_counters_consistent():
+    sc = O.OracleScene(os.path.join(GOLDEN, "g_legacy.crscene"))
+    _, c = sc.render(threads=2, count=True)
+    assert c["paths"] == sc.W * sc.H * sc.s.prefs.sample_count
+    assert c["paths"] <= c["rays"] <= c["paths"] * sc.s.prefs.bounces
+    assert c["max_depth"] <= sc.s.prefs.bounces and c["max_stack"] <= 64
+    assert c["node_pairs"] > 0 and c["tri_tests"] > 0 and c["sphere_tests"] > 0 and c["inst_visits"] > 0
+    sc.close()
+
+
+def test_srgb8_matches_reference_formula():
+    rgb = np.array([0.0, 0.001, 0.0031308, 0.2, 0.5, 1.0, 1.5, 7.0, 0.99999], dtype=np.float32)
+    rgb = np.resize(rgb, 9).astype(np.float32)
+    out = np.zeros(9, dtype=np.uint8)
+    O.lib().cro_to_srgb8(rgb.ctypes.data, out.ctypes.data, 3)
+    exp = []
+    for c in rgb:
+        s = 12.92 * c if c <= 0.0031308 else 1.055 * c ** 0.4166666667 - 0.055
+        exp.append(min(int(min(s * 255.0, 255.0)), 255))
+    assert np.abs(out.astype(int) - np.array(exp)).max() <= 1
+
+
+@pytest.mark.parametrize("name,W,H,spp,b", [("hdr", 96, 54, 4, 32), ("scene", 80, 50, 4, 4), ("refraction", 64, 36, 2, 512), ("venus", 40, 64, 4, 25)])
+def test_bundled_scenes_against_reference_framebuffers(name, W, H, spp, b):
+    """Bundled input/*.json scenes: framebuffers rendered by the strict reference in the build container
+    (scenes/_built/ref_*.f32, written by __graft_entry__.build) vs the oracle: bit-exact."""
+    ref_path = os.path.join(BUILT, f"ref_{name}_{W}x{H}x{spp}_b{b}.f32")
+    scene = os.path.join(BUILT, name + ".crscene")
+    if not (os.path.exists(ref_path) and os.path.exists(scene)):
+        pytest.skip("scenes/_built not generated (needs the build container with /root/reference)")
+    sc = O.OracleScene(scene, W, H, spp, b)
+    ref = np.fromfile(ref_path, dtype=np.float32).reshape(H, W, 3)
+    img = sc.render(threads=os.cpu_count())
+    assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+    sc.close()
