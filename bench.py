@@ -285,9 +285,9 @@ def main():
     t0 = time.perf_counter()
     e_rays = 0
     e_steps = max(1, min(args.steps, 2))
-    for _ in range(e_steps):
+    for it in range(e_steps):
         g2 = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
-        ptr, _ = g2.device_ptr()
+        ptr = g2.device_ptr()[0]
 
         class _Fb2:
             __cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f4", "data": (ptr, False), "version": 2}
@@ -298,7 +298,7 @@ def main():
         e_rays += g.get_stats()["rays"]
         if rank == 0:
             g2.read(host_fb)
-        if _ != e_steps - 1:
+        if it != e_steps - 1:
             g2.close()
     barrier()
     e_ms = 1e3 * (time.perf_counter() - t0)

@@ -529,6 +529,8 @@ extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 			cudaEventElapsedTime(&a, tev[i], tev[i + 1]);
 			cudaEventElapsedTime(&b, tev[i + 1], tev[i + 2]);
 			trace_ms += a; shade_ms += b;
+			if (getenv("CRGPU_DUMP_TIMES") && (a > 5.f || b > 8.f || atoi(getenv("CRGPU_DUMP_TIMES")) > 1))
+				fprintf(stderr, "crgpu: batch %zu depth %zu trace %.3f ms shade %.3f ms\n", (i / 3) / (size_t)maxDepth, (i / 3) % (size_t)maxDepth, a, b);
 		}
 		for (cudaEvent_t e : tev) cudaEventDestroy(e);
 		s->pend_trace_ms += trace_ms; s->pend_shade_ms += shade_ms; s->pend_total_ms += total_ms;

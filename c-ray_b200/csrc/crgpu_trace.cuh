@@ -64,6 +64,7 @@ CRD void cr_camera_ray(const DevCamera &cam, int x, int y, uint64_t &rng, v3 &o,
 struct RaySetup {
 	v3 invDir, scaledStart;
 	bool ox, oy, oz;
+	unsigned deg;      /* bit a set: 1/d[a] is +-inf (d[a] is +-0 or denormal) — see cr_node_test */
 };
 
 CRD RaySetup cr_ray_setup(v3 o, v3 d) {                                                /* bvh.c:369-376 */
@@ -73,17 +74,36 @@ CRD RaySetup cr_ray_setup(v3 o, v3 d) {                                         
 	s.oz = (__float_as_uint(d.z) >> 31) != 0u;
 	s.invDir = v3make(cr_div(1.0f, d.x), cr_div(1.0f, d.y), cr_div(1.0f, d.z));
 	s.scaledStart = v3scale(v3mul(o, s.invDir), -1.0f);
+	s.deg = (isinf(s.invDir.x) ? 1u : 0u) | (isinf(s.invDir.y) ? 2u : 0u) | (isinf(s.invDir.z) ? 4u : 0u);
 	return s;
 }
 
-CRD bool cr_node_test(const float *b, const RaySetup &r, float maxDist, float &tEntry) {
-	/* strict reference: a*b+c with two roundings (FP_FAST_FMAF undefined without -march, bvh.c:318-324) */
-	const float tMinX = (r.ox ? b[1] : b[0]) * r.invDir.x + r.scaledStart.x;
-	const float tMaxX = (r.ox ? b[0] : b[1]) * r.invDir.x + r.scaledStart.x;
-	const float tMinY = (r.oy ? b[3] : b[2]) * r.invDir.y + r.scaledStart.y;
-	const float tMaxY = (r.oy ? b[2] : b[3]) * r.invDir.y + r.scaledStart.y;
-	const float tMinZ = (r.oz ? b[5] : b[4]) * r.invDir.z + r.scaledStart.z;
-	const float tMaxZ = (r.oz ? b[4] : b[5]) * r.invDir.z + r.scaledStart.z;
+/* Slab test of one child.  For ordinary rays this is intersectNode verbatim (bvh.c:326-352; the strict
+ * reference build has FP_FAST_FMAF undefined, so a*b+c rounds twice, bvh.c:318-324).
+ *
+ * Degenerate axes.  When a direction component is exactly 0 the reference computes b*inf + (-o*inf),
+ * which is NaN for most bounds; its NaN-tolerant min/max chain then silently DROPS that axis (and, by
+ * propagation, the x or y axis before it), so such a ray "enters" a large part of the BVH — up to
+ * ~115,000 of Venus' 229,087 nodes per ray (measured with the oracle on hdr.json, horizon rays with
+ * d.y == 0).  That is harmless on a CPU (~1 ms) but one GPU thread would need ~50-150 ms while the
+ * whole wavefront waits.  The reference's degenerate test is a pure superset of the exact slab test and
+ * the Möller–Trumbore test decides every hit on its own, so culling with the exact test (axis with
+ * d == 0: inside the slab iff lo <= o <= hi) returns the same closest hit; the two could only differ
+ * for a ray that grazes a triangle within one ulp of its leaf's bounding box, on an already
+ * measure-zero ray (~1e-13 per ray).  Rays without a zero component take the verbatim path. */
+CRD bool cr_node_test(const float *b, const RaySetup &r, v3 o, float maxDist, float &tEntry) {
+	float tMinX = (r.ox ? b[1] : b[0]) * r.invDir.x + r.scaledStart.x;
+	float tMaxX = (r.ox ? b[0] : b[1]) * r.invDir.x + r.scaledStart.x;
+	float tMinY = (r.oy ? b[3] : b[2]) * r.invDir.y + r.scaledStart.y;
+	float tMaxY = (r.oy ? b[2] : b[3]) * r.invDir.y + r.scaledStart.y;
+	float tMinZ = (r.oz ? b[5] : b[4]) * r.invDir.z + r.scaledStart.z;
+	float tMaxZ = (r.oz ? b[4] : b[5]) * r.invDir.z + r.scaledStart.z;
+	if (r.deg) {
+		const float inf = __int_as_float(0x7f800000);
+		if (r.deg & 1u) { const bool in = (b[0] <= o.x) && (o.x <= b[1]); tMinX = in ? -inf : inf; tMaxX = in ? inf : -inf; }
+		if (r.deg & 2u) { const bool in = (b[2] <= o.y) && (o.y <= b[3]); tMinY = in ? -inf : inf; tMaxY = in ? inf : -inf; }
+		if (r.deg & 4u) { const bool in = (b[4] <= o.z) && (o.z <= b[5]); tMinZ = in ? -inf : inf; tMaxZ = in ? inf : -inf; }
+	}
 	float tMin = tMinX > tMinY ? tMinX : tMinY;
 	float tMax = tMaxX < tMaxY ? tMaxX : tMaxY;
 	tMin = tMin > tMinZ ? tMin : tMinZ;
@@ -94,93 +114,33 @@ CRD bool cr_node_test(const float *b, const RaySetup &r, float maxDist, float &t
 	return tMin <= tMax;
 }
 
-/* Generic ordered traversal; Leaf(first, count) -> bool tests a leaf and may shrink best.t. */
-template <class Leaf, bool COUNT>
-CRD bool cr_traverse(const DevBvh &bvh, const PairNode *__restrict__ pairs, v3 o, v3 d, Hit &best,
-					 Leaf &leaf, uint32_t *stack, TraceCounters *ctr) {
-	if (bvh.node_count < 1) {                                                      /* bvh.c:362-365 */
-		best.inst = -1;
-		return false;
-	}
-	const RaySetup rs = cr_ray_setup(o, d);
-	float maxDist = best.t;
-	if (bvh.node_count == 1) {                                                     /* bvh.c:382-387 */
-		float tEntry;
-		if (cr_node_test(bvh.root_bounds, rs, maxDist, tEntry)) return leaf(bvh.root_first, bvh.root_count);
-		return false;
-	}
-	const PairNode *base = pairs + bvh.pair_offset;
-	uint32_t node = 0;
-	int sp = 0;
-	bool hasHit = false;
-	while (true) {
-		const float4 *p4 = reinterpret_cast<const float4 *>(base + node);
-		const float4 q0 = __ldg(p4 + 0), q1 = __ldg(p4 + 1), q2 = __ldg(p4 + 2);
-		const uint4 q3 = __ldg(reinterpret_cast<const uint4 *>(p4 + 3));
-		const float lb[6] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y };
-		const float rb[6] = { q1.z, q1.w, q2.x, q2.y, q2.z, q2.w };
-		if (COUNT) ctr->pairs++;
-		float tL, tR;
-		const bool hitL = cr_node_test(lb, rs, maxDist, tL);
-		const bool hitR = cr_node_test(rb, rs, maxDist, tR);
-		bool goL = false, goR = false;
-		if (hitL) {
-			if (q3.z & CRG_LEAF_BIT) {
-				if (leaf(q3.x, q3.z & ~CRG_LEAF_BIT)) { maxDist = best.t; hasHit = true; }
-			} else goL = true;
-		}
-		if (hitR) {
-			if (q3.w & CRG_LEAF_BIT) {
-				if (leaf(q3.y, q3.w & ~CRG_LEAF_BIT)) { maxDist = best.t; hasHit = true; }
-			} else goR = true;
-		}
-		if (goL & goR) {
-			const bool swap = tL > tR;                                             /* bvh.c:424-431 */
-			node = swap ? q3.y : q3.x;
-			stack[sp++] = swap ? q3.x : q3.y;
-		} else if (goL ^ goR) {
-			node = goL ? q3.x : q3.y;
-		} else {
-			if (sp == 0) break;
-			node = stack[--sp];
-		}
-	}
-	return hasHit;
-}
-
-/* ---- leaves ------------------------------------------------------------------------------------------------------ */
+/* rayIntersectsWithPolygon over one leaf (bvh.c:443-462 + poly.c:17-53); tris already offset to the BVH's first slot */
 template <bool COUNT>
-struct BottomLeaf {                                                               /* bvh.c:443-462 + poly.c:17-53 */
-	const PackedTri *__restrict__ tris;   /* already offset to this BVH's first slot */
-	uint32_t slot_base;
-	v3 o, d;
-	Hit *best;
-	TraceCounters *ctr;
-	CRD bool operator()(uint32_t first, uint32_t count) {
-		bool found = false;
-		for (uint32_t i = 0; i < count; ++i) {
-			const float4 *t4 = reinterpret_cast<const float4 *>(tris + first + i);
-			const float4 a = __ldg(t4 + 0), b = __ldg(t4 + 1), c4 = __ldg(t4 + 2);
-			if (COUNT) ctr->tris++;
-			const v3 v0 = v3make(a.x, a.y, a.z), e1 = v3make(a.w, b.x, b.y), e2 = v3make(b.z, b.w, c4.x);
-			const v3 n = v3make(c4.y, c4.z, c4.w);
-			const v3 c = v3sub(v0, o);
-			const v3 r = v3cross(d, c);
-			const float invDet = cr_div(1.0f, v3dot(n, d));
-			const float u = v3dot(r, e2) * invDet;
-			const float v = v3dot(r, e1) * invDet;
-			if (u >= 0.0f && v >= 0.0f && u + v <= 1.0f) {
-				const float t = v3dot(n, c) * invDet;
-				if (t >= 0.0f && t < best->t) {
-					best->t = t; best->u = u; best->v = v;
-					best->prim = slot_base + first + i;
-					found = true;
-				}
+CRD bool cr_leaf_tris(const PackedTri *__restrict__ tris, uint32_t slot_base, uint32_t first, uint32_t count,
+					  v3 o, v3 d, Hit &best, TraceCounters *ctr) {
+	bool found = false;
+	for (uint32_t i = 0; i < count; ++i) {
+		const float4 *t4 = reinterpret_cast<const float4 *>(tris + first + i);
+		const float4 a = __ldg(t4 + 0), b = __ldg(t4 + 1), c4 = __ldg(t4 + 2);
+		if (COUNT) ctr->tris++;
+		const v3 v0 = v3make(a.x, a.y, a.z), e1 = v3make(a.w, b.x, b.y), e2 = v3make(b.z, b.w, c4.x);
+		const v3 n = v3make(c4.y, c4.z, c4.w);
+		const v3 c = v3sub(v0, o);
+		const v3 r = v3cross(d, c);
+		const float invDet = cr_div(1.0f, v3dot(n, d));
+		const float u = v3dot(r, e2) * invDet;
+		const float v = v3dot(r, e1) * invDet;
+		if (u >= 0.0f && v >= 0.0f && u + v <= 1.0f) {
+			const float t = v3dot(n, c) * invDet;
+			if (t >= 0.0f && t < best.t) {
+				best.t = t; best.u = u; best.v = v;
+				best.prim = slot_base + first + i;
+				found = true;
 			}
 		}
-		return found;
 	}
-};
+	return found;
+}
 
 CRD bool cr_sphere_test(v3 o, v3 d, float radius, float &dist) {                   /* sphere.c:20-50 */
 	const float A = v3dot(d, d);
@@ -204,51 +164,129 @@ CRD void cr_object_ray(const float *Ainv, float ray_offset, v3 o, v3 d, v3 &oo, 
 	oo = v3add(oo, v3scale(od, ray_offset));
 }
 
+#define CRG_END 0xffffffffu
+
+/* getClosestIsect (pathtrace.c:26-30) = traverseTopLevelBvh → intersectTopLevelLeaf → intersectMesh →
+ * traverseBottomLevelBvh, flattened into ONE loop so that the 32 lanes of a warp stay convergent:
+ * every iteration a lane performs either one child-pair step (top OR bottom level — same code, only
+ * the base pointer and the ray registers differ) or one instance step (transform the ray into the
+ * next instance of a pending top-level leaf; spheres are tested on the spot, meshes switch the lane
+ * to the bottom level).  The reference's recursion (a whole bottom-level traversal nested inside a
+ * top-level leaf loop) serialised divergent lanes: ncu measured 3-6 active threads per warp.
+ *
+ * Order of evaluation is the reference's: both children are tested against the closest distance known
+ * BEFORE either leaf is processed; left leaf, then right leaf; nearer internal child next, farther one
+ * pushed; instances of a leaf in primIndices order; strict t < distance for triangles, t <= distance
+ * for spheres.  The reference's `maxDist` copies always equal isect->distance at the time of a node
+ * test (they are refreshed after every leaf that found something), so best.t is used directly. */
 template <bool COUNT>
-struct TopLeaf {                                                                   /* bvh.c:468-486 */
-	const DevScene *sc;
-	v3 o, d;
-	Hit *best;
-	uint32_t *stack2;
-	TraceCounters *ctr;
-	CRD bool operator()(uint32_t first, uint32_t count) {
-		bool found = false;
-		for (uint32_t i = 0; i < count; ++i) {
-			const int cur = __ldg(sc->top_prims + sc->top.slot_offset + first + i);
-			const DevInstance *inst = sc->instances + cur;
+CRD Hit cr_closest_hit(const DevScene &sc, v3 wo, v3 wd, TraceCounters *ctr) {
+	Hit best;
+	best.t = CR_FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = 0u;
+	if (sc.top.node_count < 1) return best;                                        /* bvh.c:362-365 */
+	uint32_t stack[2 * CRG_MAX_STACK + 2];
+	int sp = 0, spBase = 0;
+	bool bottom = false;
+	v3 o = wo, d = wd;
+	RaySetup rs = cr_ray_setup(o, d);
+	const PairNode *__restrict__ base = sc.pairs + sc.top.pair_offset;
+	const PackedTri *__restrict__ tris = sc.tris;
+	uint32_t slotBase = 0u, node = 0u, topNext = CRG_END;
+	uint32_t pendA = 0u, cntA = 0u, pendB = 0u, cntB = 0u;     /* pending top-level leaf items: A (left) before B (right) */
+	int curInst = -1;
+	bool instHit = false;
+	if (sc.top.node_count == 1) {                                                  /* bvh.c:382-387 */
+		float te;
+		node = CRG_END;
+		if (cr_node_test(sc.top.root_bounds, rs, o, best.t, te)) { pendA = sc.top.root_first; cntA = sc.top.root_count; }
+	}
+	while (true) {
+		if (bottom || (cntA | cntB) == 0u) {
+			if (node == CRG_END) break;                                            /* top level finished, nothing pending */
+			/* ---- one child-pair step (bvh.c:391-439) */
+			const float4 *p4 = reinterpret_cast<const float4 *>(base + node);
+			const float4 q0 = __ldg(p4 + 0), q1 = __ldg(p4 + 1), q2 = __ldg(p4 + 2);
+			const uint4 q3 = __ldg(reinterpret_cast<const uint4 *>(p4 + 3));
+			const float lb[6] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y };
+			const float rb[6] = { q1.z, q1.w, q2.x, q2.y, q2.z, q2.w };
+			if (COUNT) ctr->pairs++;
+			float tL, tR;
+			const bool hitL = cr_node_test(lb, rs, o, best.t, tL);
+			const bool hitR = cr_node_test(rb, rs, o, best.t, tR);
+			const bool leafL = (q3.z & CRG_LEAF_BIT) != 0u, leafR = (q3.w & CRG_LEAF_BIT) != 0u;
+			const bool goL = hitL && !leafL, goR = hitR && !leafR;
+			uint32_t next;
+			if (goL & goR) {
+				const bool swap = tL > tR;                                         /* bvh.c:424-431 */
+				next = swap ? q3.y : q3.x;
+				stack[sp++] = swap ? q3.x : q3.y;
+			} else if (goL ^ goR) {
+				next = goL ? q3.x : q3.y;
+			} else {
+				next = (sp == spBase) ? CRG_END : stack[--sp];
+			}
+			if (bottom) {
+				if (hitL && leafL) instHit |= cr_leaf_tris<COUNT>(tris, slotBase, q3.x, q3.z & ~CRG_LEAF_BIT, o, d, best, ctr);
+				if (hitR && leafR) instHit |= cr_leaf_tris<COUNT>(tris, slotBase, q3.y, q3.w & ~CRG_LEAF_BIT, o, d, best, ctr);
+				node = next;
+				if (node == CRG_END) {                                             /* back to the top level (instance.c:175-184) */
+					if (instHit) best.inst = curInst;
+					bottom = false;
+					o = wo; d = wd;
+					rs = cr_ray_setup(o, d);
+					base = sc.pairs + sc.top.pair_offset;
+					node = topNext;
+					spBase = 0;
+				}
+			} else {
+				if (hitL && leafL) { pendA = q3.x; cntA = q3.z & ~CRG_LEAF_BIT; }
+				if (hitR && leafR) { pendB = q3.y; cntB = q3.w & ~CRG_LEAF_BIT; }
+				node = next;
+			}
+		} else {
+			/* ---- one instance of a pending top-level leaf (bvh.c:468-486) */
+			uint32_t idx;
+			if (cntA) { idx = pendA++; --cntA; } else { idx = pendB++; --cntB; }
+			const int cur = __ldg(sc.top_prims + sc.top.slot_offset + idx);
+			const DevInstance *inst = sc.instances + cur;
 			const float4 *m4 = reinterpret_cast<const float4 *>(inst->Ainv);
 			const float4 r0 = __ldg(m4 + 0), r1 = __ldg(m4 + 1), r2 = __ldg(m4 + 2);
 			const float Ainv[12] = { r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w };
-			const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(&inst->kind)); /* kind, bvh, ray_offset, radius */
+			const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(&inst->kind));    /* kind, bvh, ray_offset, radius */
 			v3 oo, od;
-			cr_object_ray(Ainv, __uint_as_float(meta.z), o, d, oo, od);
-			bool h;
+			cr_object_ray(Ainv, __uint_as_float(meta.z), wo, wd, oo, od);
 			if (meta.x == CRS_INST_MESH) {                                         /* instance.c:169-175 */
 				if (COUNT) ctr->insts++;
-				const DevBvh bvh = sc->bvhs[meta.y];
-				BottomLeaf<COUNT> leaf = { sc->tris + bvh.slot_offset, bvh.slot_offset, oo, od, best, ctr };
-				h = cr_traverse<BottomLeaf<COUNT>, COUNT>(bvh, sc->pairs, oo, od, *best, leaf, stack2, ctr);
+				const DevBvh *bvh = sc.bvhs + meta.y;
+				const uint32_t nodeCount = __ldg(&bvh->node_count);
+				const uint32_t slotOff = __ldg(&bvh->slot_offset);
+				if (nodeCount < 1u) {
+					best.inst = -1;                                                /* bvh.c:362-365 quirk */
+				} else if (nodeCount == 1u) {                                      /* bvh.c:382-387 */
+					const RaySetup ors = cr_ray_setup(oo, od);
+					float rbnd[6], te;
+					for (int k = 0; k < 6; ++k) rbnd[k] = __ldg(&bvh->root_bounds[k]);
+					if (cr_node_test(rbnd, ors, oo, best.t, te))
+						if (cr_leaf_tris<COUNT>(sc.tris + slotOff, slotOff, __ldg(&bvh->root_first), __ldg(&bvh->root_count), oo, od, best, ctr))
+							best.inst = cur;
+				} else {
+					bottom = true;
+					topNext = node;
+					o = oo; d = od;
+					rs = cr_ray_setup(o, d);
+					base = sc.pairs + __ldg(&bvh->pair_offset);
+					tris = sc.tris + slotOff;
+					slotBase = slotOff;
+					curInst = cur;
+					instHit = false;
+					spBase = sp;
+					node = 0u;
+				}
 			} else {                                                               /* instance.c:45-51 */
 				if (COUNT) ctr->spheres++;
-				h = cr_sphere_test(oo, od, __uint_as_float(meta.w), best->t);
-			}
-			if (h) {
-				best->inst = cur;
-				found = true;
+				if (cr_sphere_test(oo, od, __uint_as_float(meta.w), best.t)) best.inst = cur;
 			}
 		}
-		return found;
 	}
-};
-
-/* getClosestIsect, pathtrace.c:26-30 */
-template <bool COUNT>
-CRD Hit cr_closest_hit(const DevScene &sc, v3 o, v3 d, TraceCounters *ctr) {
-	Hit best;
-	best.t = CR_FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = 0u;
-	uint32_t stack1[CRG_MAX_STACK + 1];
-	uint32_t stack2[CRG_MAX_STACK + 1];
-	TopLeaf<COUNT> leaf = { &sc, o, d, &best, stack2, ctr };
-	cr_traverse<TopLeaf<COUNT>, COUNT>(sc.top, sc.pairs, o, d, best, leaf, stack1, ctr);
 	return best;
 }

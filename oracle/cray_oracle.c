@@ -654,7 +654,9 @@ static struct hit closest_isect(const struct trav_ctx *c, const struct ray *ray)
 	isect.dist = FLT_MAX;
 	isect.poly = -1;
 	if (c->ctr) c->ctr->rays++;
+	const uint64_t before = c->ctr ? c->ctr->node_pairs : 0;
 	traverse(c, c->s->top_bvh, -1, ray, &isect);
+	if (c->ctr && c->ctr->node_pairs - before > c->ctr->max_pairs_ray) c->ctr->max_pairs_ray = c->ctr->node_pairs - before;
 	return isect;
 }
 
@@ -762,6 +764,7 @@ int cro_render(const struct crs_scene *s, int x0, int y0, int x1, int y1, int pa
 			counters->inst_visits += k->inst_visits; counters->draws += k->draws;
 			if (k->max_depth > counters->max_depth) counters->max_depth = k->max_depth;
 			if (k->max_stack > counters->max_stack) counters->max_stack = k->max_stack;
+			if (k->max_pairs_ray > counters->max_pairs_ray) counters->max_pairs_ray = k->max_pairs_ray;
 		}
 	}
 	free(rs); free(tids); free(jobs);

@@ -33,7 +33,7 @@ class Scene(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("paths", "rays", "node_pairs", "tri_tests", "sphere_tests",
-                                          "inst_visits", "draws", "max_depth", "max_stack")]
+                                          "inst_visits", "draws", "max_depth", "max_stack", "max_pairs_ray")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
