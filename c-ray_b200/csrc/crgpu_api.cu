@@ -413,6 +413,8 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 		}
 		DevTexture d;
 		d.width = t.width; d.height = t.height; d.channels = t.channels; d.is_float = t.is_float; d.has_alpha = t.has_alpha; d.pad = 0;
+		d.wmask = (t.width & (t.width - 1u)) == 0u ? t.width - 1u : 0u;
+		d.hmask = (t.height & (t.height - 1u)) == 0u ? t.height - 1u : 0u;
 		d.data = texdata + t.data_offset;
 		texs[i] = d;
 	}
@@ -441,6 +443,11 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	FAIL_IF(upload(s, mats, &d.materials));
 	FAIL_IF(upload(s, nodes, &d.nodes));
 	FAIL_IF(upload(s, texs, &d.textures));
+	{
+		std::vector<float> lut(256);
+		for (int i = 0; i < 256; ++i) { volatile float num = (float)i, den = 255.0f; lut[i] = num / den; }   /* IEEE divss == __fdiv_rn */
+		FAIL_IF(upload(s, lut, &d.u8_to_unit));
+	}
 
 	CUS(cudaMalloc((void **)&s->dev_copy, sizeof(DevScene)));
 	s->allocs.push_back(s->dev_copy);
@@ -448,9 +455,10 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	s->fb_floats = (size_t)d.image_width * d.image_height * 3u;
 	CUS(cudaMalloc((void **)&s->fb, s->fb_floats * sizeof(float)));
 	CUS(cudaMemset(s->fb, 0, s->fb_floats * sizeof(float)));
-	CUS(cudaMalloc((void **)&s->wb.counts, 2 * sizeof(unsigned)));
-	CUS(cudaMalloc((void **)&s->wb.stats, 8 * sizeof(unsigned long long)));
-	CUS(cudaMemset(s->wb.stats, 0, 8 * sizeof(unsigned long long)));
+	CUS(cudaMalloc((void **)&s->wb.counts, 4 * sizeof(unsigned)));
+	CUS(cudaMemset(s->wb.counts, 0, 4 * sizeof(unsigned)));
+	CUS(cudaMalloc((void **)&s->wb.stats, 80 * sizeof(unsigned long long)));
+	CUS(cudaMemset(s->wb.stats, 0, 80 * sizeof(unsigned long long)));
 	CUS(cudaDeviceSynchronize());
 #undef FAIL_IF
 #undef CUS
@@ -545,6 +553,10 @@ extern "C" int crgpu_get_stats(crgpu_scene *s, struct crgpu_stats *stats) {
 	unsigned long long h[8];
 	CU(cudaMemcpyAsync(h, s->wb.stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
 	CU(cudaStreamSynchronize(s->stream));
+	if (h[7] != s->fetched[7]) {
+		memcpy(s->fetched, h, sizeof h);
+		return fail(CRGPU_ERR_CUDA, "traversal watchdog: %llu ray(s) exceeded the step limit (corrupt BVH?)", h[7]);
+	}
 	if (stats) {
 		memset(stats, 0, sizeof *stats);
 		stats->paths = s->pend_paths;

@@ -33,7 +33,15 @@ CRN float cr_sinf(float x) { return (float)sin((double)x); }
 CRN float cr_cosf(float x) { return (float)cos((double)x); }
 CRN float2 cr_sincosf2(float x) { double ds, dc; sincos((double)x, &ds, &dc); return make_float2((float)ds, (float)dc); }
 CRD void cr_sincosf(float x, float *s, float *c) { const float2 r = cr_sincosf2(x); *s = r.x; *c = r.y; }
-CRN float cr_powf(float x, float y) { return (float)pow((double)x, (double)y); }
+/* powf(x, y): fp64 evaluation rounded once.  For x > 0 it is exp(y*log(x)) (relative error ~1e-15, i.e. the
+ * fp32 result differs from the correctly rounded one for ~1e-8 of inputs — glibc's own powf is off more often);
+ * everything else (zero, negative, inf, nan) goes through the full pow() special-case logic. */
+CRN float cr_powf(float x, float y) {
+	if (x > 0.0f && x < CR_FLT_MAX && y == y && fabsf(y) < 1.0e6f) return (float)exp((double)y * log((double)x));
+	return (float)pow((double)x, (double)y);
+}
+/* powf(x, 5.0f) as used by schlick() (vector.h:271): four fp64 products, one rounding */
+CRD float cr_pow5f(float x) { const double a = (double)x, a2 = a * a; return (float)(a2 * a2 * a); }
 CRN float cr_logf(float x) { return (float)log((double)x); }
 CRN float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
 CRN float cr_acosf(float x) { return (float)acos((double)x); }

@@ -71,7 +71,10 @@ struct DevMaterial {
 };
 
 struct DevTexture {
-	uint32_t width, height, channels, is_float, has_alpha, pad;
+	uint32_t width, height, channels, is_float, has_alpha;
+	uint32_t wmask, hmask;          /* width-1 / height-1 when that dimension is a power of two, else 0 (x % W == x & (W-1), also for the
+	                                   2^64-wrapped negative coordinates of texture.c:34-35) */
+	uint32_t pad;
 	const uint8_t *data;
 };
 
@@ -98,4 +101,5 @@ struct DevScene {
 	const DevMaterial*materials;
 	const crs_node   *nodes;
 	const DevTexture *textures;
+	const float      *u8_to_unit;   /* [256]: (float)i / 255.0f, the byte→float division of texture.c:48-60 done once */
 };

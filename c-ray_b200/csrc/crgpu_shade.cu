@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256) k_shade(const DevScene *__restrict__ scp,
 	const DevScene &sc = *scp;
 	const unsigned n = wb.counts[cur];
 	const int nxt = cur ^ 1;
+	if (blockIdx.x == 0 && threadIdx.x == 0) wb.counts[2] = 0u;   /* K2's work counter, for the next bounce */
 	const unsigned lane = threadIdx.x & 31u;
 	/* whole warps iterate together so the ballot below is convergent */
 	const unsigned stride = gridDim.x * blockDim.x;

@@ -35,14 +35,22 @@ struct Rec {                  /* the fields of struct hitRecord (hitrecord.h:14-
 struct BsdfSample { v3 out; col4 color; };
 
 /* ---- texture.c:32-63 ------------------------------------------------------------------------------------------ */
-CRD col4 cr_texel(const DevTexture &t, uint64_t x, uint64_t y) {
-	x = x % t.width;
-	y = y % t.height;
-	const size_t idx = (size_t)((x + ((uint64_t)(t.height - 1) - y) * t.width) * t.channels);
+/* x % extent for the size_t coordinates of textureGetPixelInternal (negative ints arrive sign-extended) */
+CRD uint32_t cr_wrap(uint64_t x, uint32_t extent, uint32_t mask) {
+	if (mask) return (uint32_t)x & mask;
+	if ((x >> 32) == 0ull) return (uint32_t)x % extent;
+	return (uint32_t)(x % extent);
+}
+
+CRD col4 cr_texel(const DevScene &sc, const DevTexture &t, uint64_t x64, uint64_t y64) {
+	const uint32_t x = cr_wrap(x64, t.width, t.wmask);
+	const uint32_t y = cr_wrap(y64, t.height, t.hmask);
+	const size_t idx = ((size_t)x + (size_t)((t.height - 1u) - y) * t.width) * t.channels;
+	const float *__restrict__ lut = sc.u8_to_unit;
 	col4 o;
 	if (t.channels == 1) {
 		if (t.is_float) o.r = __ldg(reinterpret_cast<const float *>(t.data) + idx);
-		else o.r = cr_div((float)__ldg(t.data + idx), 255.0f);
+		else o.r = __ldg(lut + __ldg(t.data + idx));
 		o.g = o.r; o.b = o.r; o.a = 1.0f;
 	} else if (t.is_float) {
 		const float *f = reinterpret_cast<const float *>(t.data);
@@ -50,55 +58,54 @@ CRD col4 cr_texel(const DevTexture &t, uint64_t x, uint64_t y) {
 		o.a = t.has_alpha ? __ldg(f + idx + 3) : 1.0f;
 	} else if (t.channels == 4) {
 		const uchar4 px = __ldg(reinterpret_cast<const uchar4 *>(t.data + idx));
-		o.r = cr_div((float)px.x, 255.0f); o.g = cr_div((float)px.y, 255.0f); o.b = cr_div((float)px.z, 255.0f);
-		o.a = cr_div((float)px.w, 255.0f);
+		o.r = __ldg(lut + px.x); o.g = __ldg(lut + px.y); o.b = __ldg(lut + px.z); o.a = __ldg(lut + px.w);
 	} else {
-		o.r = cr_div((float)__ldg(t.data + idx), 255.0f);
-		o.g = cr_div((float)__ldg(t.data + idx + 1), 255.0f);
-		o.b = cr_div((float)__ldg(t.data + idx + 2), 255.0f);
-		o.a = t.has_alpha ? cr_div((float)__ldg(t.data + idx + 3), 255.0f) : 1.0f;
+		o.r = __ldg(lut + __ldg(t.data + idx));
+		o.g = __ldg(lut + __ldg(t.data + idx + 1));
+		o.b = __ldg(lut + __ldg(t.data + idx + 2));
+		o.a = t.has_alpha ? __ldg(lut + __ldg(t.data + idx + 3)) : 1.0f;
 	}
 	return o;
 }
 
 /* alpha lane only (same arithmetic as cr_texel().a) */
-CRD float cr_texel_alpha(const DevTexture &t, uint64_t x, uint64_t y) {
+CRD float cr_texel_alpha(const DevScene &sc, const DevTexture &t, uint64_t x64, uint64_t y64) {
 	if (!t.has_alpha || t.channels != 4) return 1.0f;
-	x = x % t.width;
-	y = y % t.height;
-	const size_t idx = (size_t)((x + ((uint64_t)(t.height - 1) - y) * t.width) * 4u);
+	const uint32_t x = cr_wrap(x64, t.width, t.wmask);
+	const uint32_t y = cr_wrap(y64, t.height, t.hmask);
+	const size_t idx = ((size_t)x + (size_t)((t.height - 1u) - y) * t.width) * 4u;
 	if (t.is_float) return __ldg(reinterpret_cast<const float *>(t.data) + idx + 3);
-	return cr_div((float)__ldg(t.data + idx + 3), 255.0f);
+	return __ldg(sc.u8_to_unit + __ldg(t.data + idx + 3));
 }
 
-CRD col4 cr_texture_get(const DevTexture &t, float x, float y, bool filtered) {             /* texture.c:66-79 */
-	if (!filtered) return cr_texel(t, cr_f2sz(x), cr_f2sz(y));
+CRD col4 cr_texture_get(const DevScene &sc, const DevTexture &t, float x, float y, bool filtered) {             /* texture.c:66-79 */
+	if (!filtered) return cr_texel(sc, t, cr_f2sz(x), cr_f2sz(y));
 	x = x * (float)t.width;
 	y = y * (float)t.height;
 	const float xcopy = x - 0.5f;
 	const float ycopy = y - 0.5f;
 	const int xint = cr_f2i(xcopy);
 	const int yint = cr_f2i(ycopy);
-	const col4 tl = cr_texel(t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)yint);
-	const col4 tr = cr_texel(t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)yint);
-	const col4 bl = cr_texel(t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)(yint + 1));
-	const col4 br = cr_texel(t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)(yint + 1));
+	const col4 tl = cr_texel(sc, t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)yint);
+	const col4 tr = cr_texel(sc, t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)yint);
+	const col4 bl = cr_texel(sc, t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)(yint + 1));
+	const col4 br = cr_texel(sc, t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)(yint + 1));
 	const float fx = xcopy - (float)xint, fy = ycopy - (float)yint;
 	return c4mix(c4mix(tl, tr, fx), c4mix(bl, br, fx), fy);
 }
 
-CRD float cr_texture_get_alpha(const DevTexture &t, float x, float y, bool filtered) {
-	if (!filtered) return cr_texel_alpha(t, cr_f2sz(x), cr_f2sz(y));
+CRD float cr_texture_get_alpha(const DevScene &sc, const DevTexture &t, float x, float y, bool filtered) {
+	if (!filtered) return cr_texel_alpha(sc, t, cr_f2sz(x), cr_f2sz(y));
 	x = x * (float)t.width;
 	y = y * (float)t.height;
 	const float xcopy = x - 0.5f;
 	const float ycopy = y - 0.5f;
 	const int xint = cr_f2i(xcopy);
 	const int yint = cr_f2i(ycopy);
-	const float tl = cr_texel_alpha(t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)yint);
-	const float tr = cr_texel_alpha(t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)yint);
-	const float bl = cr_texel_alpha(t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)(yint + 1));
-	const float br = cr_texel_alpha(t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)(yint + 1));
+	const float tl = cr_texel_alpha(sc, t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)yint);
+	const float tr = cr_texel_alpha(sc, t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)yint);
+	const float bl = cr_texel_alpha(sc, t, (uint64_t)(int64_t)xint, (uint64_t)(int64_t)(yint + 1));
+	const float br = cr_texel_alpha(sc, t, (uint64_t)(int64_t)(xint + 1), (uint64_t)(int64_t)(yint + 1));
 	const float fx = xcopy - (float)xint, fy = ycopy - (float)yint;
 	const float top = tl * (1.0f - fx) + tr * fx;
 	const float bot = bl * (1.0f - fx) + br * fx;
@@ -119,9 +126,9 @@ static __device__ __noinline__ col4 cr_image_color(const DevScene &sc, const crs
 	if (n.options & CRS_IMG_NO_BILINEAR) {
 		const float x = rec.uv.x * (float)t.width;
 		const float y = rec.uv.y * (float)t.height;
-		out = cr_texture_get(t, x, y, false);
+		out = cr_texture_get(sc, t, x, y, false);
 	} else {
-		out = cr_texture_get(t, rec.uv.x, rec.uv.y, true);
+		out = cr_texture_get(sc, t, rec.uv.x, rec.uv.y, true);
 	}
 	if (n.options & CRS_IMG_SRGB_TRANSFORM)
 		out = c4make(cr_srgb_to_linear(out.r), cr_srgb_to_linear(out.g), cr_srgb_to_linear(out.b), out.a);
@@ -132,8 +139,8 @@ static __device__ __noinline__ float cr_image_alpha(const DevScene &sc, const cr
 	if (n.tex < 0) return 1.0f;
 	const DevTexture t = sc.textures[n.tex];
 	if (n.options & CRS_IMG_NO_BILINEAR)
-		return cr_texture_get_alpha(t, rec.uv.x * (float)t.width, rec.uv.y * (float)t.height, false);
-	return cr_texture_get_alpha(t, rec.uv.x, rec.uv.y, true);
+		return cr_texture_get_alpha(sc, t, rec.uv.x * (float)t.width, rec.uv.y * (float)t.height, false);
+	return cr_texture_get_alpha(sc, t, rec.uv.x, rec.uv.y, true);
 }
 
 CRD col4 cr_gradient(const crs_node &n, const Rec &rec) {                                   /* gradient.c:40-45 */
@@ -233,7 +240,7 @@ CRD bool cr_refract(v3 in, v3 normal, float niOverNt, v3 &refracted) {
 CRD float cr_schlick(float cosine, float IOR) {
 	float r0 = cr_div(1.0f - IOR, 1.0f + IOR);
 	r0 = r0 * r0;
-	return r0 + (1.0f - r0) * cr_powf(1.0f - cosine, 5.0f);
+	return r0 + (1.0f - r0) * cr_pow5f(1.0f - cosine);
 }
 /* shared by glass.c:53-67 and plastic.c:60-74 */
 CRD float cr_fresnel_probability(const Rec &rec, float IOR, v3 &refracted) {

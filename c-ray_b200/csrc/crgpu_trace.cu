@@ -23,20 +23,69 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
 		wb.stC[0][id] = make_uint4(__float_as_uint(1.0f), id, (unsigned)(rng & 0xffffffffull), (unsigned)(rng >> 32));
 		wb.L[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counts[0] = n; wb.counts[1] = 0u; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counts[0] = n; wb.counts[1] = 0u; wb.counts[2] = 0u; }
 }
 
-/* ---- K2 ------------------------------------------------------------------------------------------------------------ */
+/* ---- K2: persistent warps with dynamic ray refill ----------------------------------------------------------------------
+ * Ray lengths vary a lot (hdr.json: 7 child-pair steps on average, >200 for some), so a warp that takes 32
+ * rays and waits for the slowest one idles most lanes (ncu: 7-10 active threads/warp).  Here every warp keeps
+ * its 32 traversal state machines in registers and, whenever fewer than CRG_REFILL lanes are busy, pulls new
+ * rays for the idle lanes from a global work counter (one ballot + one atomicAdd per refill, indices handed
+ * out in lane order so neighbouring lanes still get neighbouring — coherent — rays). */
+#define CRG_REFILL 24
+#define CRG_MAX_STEPS 8000000u   /* > 30x the node count of any scene that fits the 2^23-node address space we support */
+
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int cur) {
 	const unsigned n = wb.counts[cur];
+	const unsigned lane = threadIdx.x & 31u;
+	const float4 *__restrict__ stA = wb.stA[cur];
+	const float4 *__restrict__ stB = wb.stB[cur];
 	TraceCounters tc = { 0u, 0u, 0u, 0u };
-	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const float4 a = wb.stA[cur][i];
-		const float4 b = wb.stB[cur][i];
-		const Hit h = cr_closest_hit<COUNT>(sc, v3make(a.x, a.y, a.z), v3make(a.w, b.x, b.y), &tc);
-		wb.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-		wb.hitInst[i] = h.inst;
+	uint32_t stack[2 * CRG_MAX_STACK + 2];
+	Traversal<COUNT> tr;
+	tr.stack = stack;
+	tr.begin(sc, v3make(0.f, 0.f, 0.f), v3make(0.f, 0.f, 1.f));   /* every lane holds a VALID (idle) state from the start */
+	bool busy = false;
+	bool exhausted = false;          /* warp-uniform: the work counter ran past n */
+	unsigned ray = 0u;
+	unsigned steps = 0u;             /* safety net: a lane that exceeds CRG_MAX_STEPS is abandoned and flagged */
+	while (true) {
+		unsigned active = __ballot_sync(0xffffffffu, busy);
+		if (!exhausted && __popc(active) < CRG_REFILL) {
+			const unsigned idle = ~active;
+			const unsigned nidle = (unsigned)__popc(idle);
+			unsigned base = 0u;
+			if (lane == 0u) base = atomicAdd(&wb.counts[2], nidle);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base + nidle >= n) exhausted = true;
+			const unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+			if (!busy && i < n) {
+				const float4 a = stA[i];
+				const float4 b = stB[i];
+				ray = i;
+				steps = 0u;
+				tr.begin(sc, v3make(a.x, a.y, a.z), v3make(a.w, b.x, b.y));
+				busy = true;
+			}
+			active = __ballot_sync(0xffffffffu, busy);
+		}
+		if (active == 0u) break;         /* nothing in flight and nothing left to fetch */
+		if (busy) {
+			if (tr.done()) {
+				wb.hit[ray] = make_float4(tr.best.t, tr.best.u, tr.best.v, __uint_as_float(tr.best.prim));
+				wb.hitInst[ray] = tr.best.inst;
+				busy = false;
+			} else {
+				tr.step(sc, &tc);
+				if (++steps > CRG_MAX_STEPS) {   /* cannot happen for a finite BVH; never hang the GPU */
+					atomicAdd(&wb.stats[7], 1ull);
+					wb.hit[ray] = make_float4(CR_FLT_MAX, 0.f, 0.f, 0.f);
+					wb.hitInst[ray] = -1;
+					busy = false;
+				}
+			}
+		}
 	}
 	if (COUNT) {
 		atomicAdd(&wb.stats[1], (unsigned long long)tc.pairs);
@@ -49,7 +98,6 @@ __global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int 
 		wb.counts[cur ^ 1] = 0u;   /* K3 of this bounce appends survivors there */
 	}
 }
-
 
 void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDesc &td, int grid, cudaStream_t st) {
 	k_generate<<<grid, 256, 0, st>>>(sc, wb, td);

@@ -180,29 +180,43 @@ CRD void cr_object_ray(const float *Ainv, float ray_offset, v3 o, v3 d, v3 &oo, 
  * for spheres.  The reference's `maxDist` copies always equal isect->distance at the time of a node
  * test (they are refreshed after every leaf that found something), so best.t is used directly. */
 template <bool COUNT>
-CRD Hit cr_closest_hit(const DevScene &sc, v3 wo, v3 wd, TraceCounters *ctr) {
+struct Traversal {
 	Hit best;
-	best.t = CR_FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = 0u;
-	if (sc.top.node_count < 1) return best;                                        /* bvh.c:362-365 */
-	uint32_t stack[2 * CRG_MAX_STACK + 2];
-	int sp = 0, spBase = 0;
-	bool bottom = false;
-	v3 o = wo, d = wd;
-	RaySetup rs = cr_ray_setup(o, d);
-	const PairNode *__restrict__ base = sc.pairs + sc.top.pair_offset;
-	const PackedTri *__restrict__ tris = sc.tris;
-	uint32_t slotBase = 0u, node = 0u, topNext = CRG_END;
-	uint32_t pendA = 0u, cntA = 0u, pendB = 0u, cntB = 0u;     /* pending top-level leaf items: A (left) before B (right) */
-	int curInst = -1;
-	bool instHit = false;
-	if (sc.top.node_count == 1) {                                                  /* bvh.c:382-387 */
-		float te;
-		node = CRG_END;
-		if (cr_node_test(sc.top.root_bounds, rs, o, best.t, te)) { pendA = sc.top.root_first; cntA = sc.top.root_count; }
+	v3 wo, wd;             /* world ray */
+	v3 o, d;               /* ray of the current level */
+	RaySetup rs;
+	const PairNode *__restrict__ base;
+	const PackedTri *__restrict__ tris;
+	uint32_t slotBase, node, topNext;
+	uint32_t pendA, cntA, pendB, cntB;     /* pending top-level leaf items: A (left leaf) before B (right leaf) */
+	int sp, spBase, curInst;
+	bool bottom, instHit;
+	uint32_t *stack;       /* 2*CRG_MAX_STACK+2 entries of thread-local memory, owned by the caller (keeps the scalars in registers) */
+
+	CRD bool done() const { return !bottom && (cntA | cntB) == 0u && node == CRG_END; }
+
+	CRD void begin(const DevScene &sc, v3 ro, v3 rd) {
+		best.t = CR_FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = 0u;
+		wo = ro; wd = rd; o = ro; d = rd;
+		rs = cr_ray_setup(o, d);
+		base = sc.pairs + sc.top.pair_offset;
+		tris = sc.tris;
+		slotBase = 0u; node = 0u; topNext = CRG_END;
+		pendA = 0u; cntA = 0u; pendB = 0u; cntB = 0u;
+		sp = 0; spBase = 0; curInst = -1;
+		bottom = false; instHit = false;
+		if (sc.top.node_count < 1) {                                               /* bvh.c:362-365 */
+			node = CRG_END;
+		} else if (sc.top.node_count == 1) {                                       /* bvh.c:382-387 */
+			float te;
+			node = CRG_END;
+			if (cr_node_test(sc.top.root_bounds, rs, o, best.t, te)) { pendA = sc.top.root_first; cntA = sc.top.root_count; }
+		}
 	}
-	while (true) {
+
+	/* one iteration of the flat loop; precondition: !done() */
+	CRD void step(const DevScene &sc, TraceCounters *ctr) {
 		if (bottom || (cntA | cntB) == 0u) {
-			if (node == CRG_END) break;                                            /* top level finished, nothing pending */
 			/* ---- one child-pair step (bvh.c:391-439) */
 			const float4 *p4 = reinterpret_cast<const float4 *>(base + node);
 			const float4 q0 = __ldg(p4 + 0), q1 = __ldg(p4 + 1), q2 = __ldg(p4 + 2);
@@ -288,5 +302,14 @@ CRD Hit cr_closest_hit(const DevScene &sc, v3 wo, v3 wd, TraceCounters *ctr) {
 			}
 		}
 	}
-	return best;
+};
+
+template <bool COUNT>
+CRD Hit cr_closest_hit(const DevScene &sc, v3 wo, v3 wd, TraceCounters *ctr) {
+	uint32_t stack[2 * CRG_MAX_STACK + 2];
+	Traversal<COUNT> tr;
+	tr.stack = stack;
+	tr.begin(sc, wo, wd);
+	while (!tr.done()) tr.step(sc, ctr);
+	return tr.best;
 }

@@ -31,7 +31,7 @@ struct WaveBuffers {
 	float4 *hit;
 	int    *hitInst;
 	float4 *L;
-	unsigned *counts;       /* [0],[1]: live counts of the ping-pong halves */
+	unsigned *counts;       /* [0],[1]: live counts of the ping-pong halves; [2]: K2's work counter (next ray to hand out) */
 	unsigned long long *stats; /* [0] rays, [1] pairs, [2] tris, [3] spheres, [4] insts */
 };
 
