@@ -206,7 +206,7 @@ static int alloc_wave(crgpu_scene *s, uint64_t paths) {
 	if (paths <= s->cap_paths) return CRGPU_OK;
 	WaveBuffers &w = s->wb;
 	void **ptrs[] = { (void **)&w.stA[0], (void **)&w.stA[1], (void **)&w.stB[0], (void **)&w.stB[1], (void **)&w.stC[0],
-					  (void **)&w.stC[1], (void **)&w.hit, (void **)&w.hitInst, (void **)&w.L };
+					  (void **)&w.stC[1], (void **)&w.hit, (void **)&w.hitInst, (void **)&w.L, (void **)&w.hitKey, (void **)&w.perm };
 	for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
 	s->cap_paths = 0;
 	const size_t n = (size_t)paths;
@@ -215,6 +215,7 @@ static int alloc_wave(crgpu_scene *s, uint64_t paths) {
 	CU(cudaMalloc((void **)&w.stC[0], n * 16)); CU(cudaMalloc((void **)&w.stC[1], n * 16));
 	CU(cudaMalloc((void **)&w.hit, n * 16)); CU(cudaMalloc((void **)&w.hitInst, n * 4));
 	CU(cudaMalloc((void **)&w.L, n * 16));
+	CU(cudaMalloc((void **)&w.hitKey, n)); CU(cudaMalloc((void **)&w.perm, n * 4));
 	s->cap_paths = paths;
 	return CRGPU_OK;
 }
@@ -226,7 +227,7 @@ extern "C" int crgpu_scene_destroy(crgpu_scene *s) {
 	if (s->own_stream && s->own_stream != s->stream) cudaStreamSynchronize(s->own_stream);
 	for (void *p : s->allocs) cudaFree(p);
 	WaveBuffers &w = s->wb;
-	void *ptrs[] = { w.stA[0], w.stA[1], w.stB[0], w.stB[1], w.stC[0], w.stC[1], w.hit, w.hitInst, w.L, w.counts, w.stats, s->fb, s->fb8 };
+	void *ptrs[] = { w.stA[0], w.stA[1], w.stB[0], w.stB[1], w.stC[0], w.stC[1], w.hit, w.hitInst, w.L, w.hitKey, w.perm, w.hist, w.counts, w.stats, s->fb, s->fb8 };
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
 	if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -455,6 +456,8 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	s->fb_floats = (size_t)d.image_width * d.image_height * 3u;
 	CUS(cudaMalloc((void **)&s->fb, s->fb_floats * sizeof(float)));
 	CUS(cudaMemset(s->fb, 0, s->fb_floats * sizeof(float)));
+	CUS(cudaMalloc((void **)&s->wb.hist, 512 * sizeof(unsigned)));
+	CUS(cudaMemset(s->wb.hist, 0, 512 * sizeof(unsigned)));
 	CUS(cudaMalloc((void **)&s->wb.counts, 4 * sizeof(unsigned)));
 	CUS(cudaMemset(s->wb.counts, 0, 4 * sizeof(unsigned)));
 	CUS(cudaMalloc((void **)&s->wb.stats, 80 * sizeof(unsigned long long)));
@@ -517,9 +520,10 @@ extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
 			crg_launch_trace(s->dev, s->wb, cur, count, grid, st);
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
+			crg_launch_bucket(s->wb, cur, grid, st);
 			crg_launch_shade(s->dev_copy, s->wb, cur, depth, maxDepth, grid, st);
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
-			launches += 2;
+			launches += 3;
 			cur ^= 1;
 		}
 		crg_launch_accumulate(s->fb, s->wb.L, td, (int)s->dev.image_width, (int)s->dev.image_height, grid, st); ++launches;

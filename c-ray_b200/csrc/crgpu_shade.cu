@@ -6,23 +6,62 @@
 #include "crgpu_wave.cuh"
 #include "crgpu_shade.cuh"
 
-/* ---- K3 (+K4 compaction) ---------------------------------------------------------------------------------------------- */
+/* ---- K4: counting sort of the live rays by shading bucket --------------------------------------------------------------------
+ * K2 left the bucket sizes in wb.hist[0..255].  Every block derives the same exclusive prefix, then ranks
+ * its rays inside the block with shared-memory atomics and reserves one contiguous range per non-empty bucket
+ * with ONE global atomicAdd (cursor = wb.hist[256+k]).  Output: perm[bucket_base + rank] = live index.
+ * Order inside a bucket is arbitrary; results do not depend on it (every path carries its own RNG + id). */
+#define CRG_BUCKET_ITEMS 8
+__global__ void __launch_bounds__(256) k_bucket(WaveBuffers wb, int cur) {
+	__shared__ unsigned s_base[256], s_cnt[256], s_off[256];
+	const unsigned n = wb.counts[cur];
+	const unsigned t = threadIdx.x;
+	s_cnt[t] = wb.hist[t];
+	__syncthreads();
+	if (t == 0u) { unsigned acc = 0u; for (int k = 0; k < 256; ++k) { s_base[k] = acc; acc += s_cnt[k]; } }
+	__syncthreads();
+	const unsigned chunk = 256u * CRG_BUCKET_ITEMS;
+	for (unsigned c0 = blockIdx.x * chunk; c0 < n; c0 += gridDim.x * chunk) {
+		s_cnt[t] = 0u;
+		__syncthreads();
+		unsigned key[CRG_BUCKET_ITEMS], rank[CRG_BUCKET_ITEMS];
+#pragma unroll
+		for (int k = 0; k < CRG_BUCKET_ITEMS; ++k) {
+			const unsigned i = c0 + (unsigned)k * 256u + t;
+			key[k] = 0xffffffffu;
+			if (i < n) { key[k] = wb.hitKey[i]; rank[k] = atomicAdd(&s_cnt[key[k]], 1u); }
+		}
+		__syncthreads();
+		s_off[t] = s_cnt[t] ? atomicAdd(&wb.hist[256u + t], s_cnt[t]) : 0u;
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < CRG_BUCKET_ITEMS; ++k) {
+			const unsigned i = c0 + (unsigned)k * 256u + t;
+			if (key[k] != 0xffffffffu) wb.perm[s_base[key[k]] + s_off[key[k]] + rank[k]] = i;
+		}
+		__syncthreads();
+	}
+}
+
+/* ---- K3 (+ compaction) ---------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(256) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth) {
 	const DevScene &sc = *scp;
 	const unsigned n = wb.counts[cur];
 	const int nxt = cur ^ 1;
 	if (blockIdx.x == 0 && threadIdx.x == 0) wb.counts[2] = 0u;   /* K2's work counter, for the next bounce */
+	if (blockIdx.x == 0) { wb.hist[threadIdx.x] = 0u; wb.hist[256 + threadIdx.x] = 0u; }   /* K2/K4 histogram + cursors (blockDim.x == 256) */
 	const unsigned lane = threadIdx.x & 31u;
 	/* whole warps iterate together so the ballot below is convergent */
 	const unsigned stride = gridDim.x * blockDim.x;
 	const unsigned nround = (n + 31u) & ~31u;
-	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+	for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += stride) {
 		bool alive = false;
 		v3 p_next = v3make(0, 0, 0), d_next = v3make(0, 0, 0);
 		float wr = 0.f, wg = 0.f, wbl = 0.f;
 		unsigned id = 0u;
 		uint64_t rng = 0ull;
-		if (i < n) {
+		if (j < n) {
+			const unsigned i = wb.perm[j];                       /* bucket order: a warp shades one material */
 			const float4 a = wb.stA[cur][i];
 			const float4 b = wb.stB[cur][i];
 			const uint4 c = wb.stC[cur][i];
@@ -160,6 +199,9 @@ __global__ void k_kat(const DevScene *__restrict__ scp, const int32_t *__restric
 	outv[i] = k;
 }
 
+void crg_launch_bucket(const WaveBuffers &wb, int cur, int grid, cudaStream_t st) {
+	k_bucket<<<grid, 256, 0, st>>>(wb, cur);
+}
 void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int grid, cudaStream_t st) {
 	k_shade<<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
 }

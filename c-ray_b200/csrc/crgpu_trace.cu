@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
 		wb.L[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counts[0] = n; wb.counts[1] = 0u; wb.counts[2] = 0u; }
+	if (blockIdx.x == 0) { wb.hist[threadIdx.x] = 0u; wb.hist[256 + threadIdx.x] = 0u; }   /* blockDim.x == 256 */
 }
 
 /* ---- K2: persistent warps with dynamic ray refill ----------------------------------------------------------------------
@@ -42,6 +43,9 @@ __global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int 
 	const float4 *__restrict__ stA = wb.stA[cur];
 	const float4 *__restrict__ stB = wb.stB[cur];
 	TraceCounters tc = { 0u, 0u, 0u, 0u };
+	__shared__ unsigned s_hist[256];
+	s_hist[threadIdx.x] = 0u;            /* blockDim.x == 256 */
+	__syncthreads();
 	uint32_t stack[2 * CRG_MAX_STACK + 2];
 	Traversal<COUNT> tr;
 	tr.stack = stack;
@@ -75,6 +79,16 @@ __global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int 
 			if (tr.done()) {
 				wb.hit[ray] = make_float4(tr.best.t, tr.best.u, tr.best.v, __uint_as_float(tr.best.prim));
 				wb.hitInst[ray] = tr.best.inst;
+				unsigned key = 0u;                                   /* shading bucket for K4/K3 */
+				if (tr.best.inst >= 0) {
+					const DevInstance *inst = sc.instances + tr.best.inst;
+					unsigned material;
+					if (__ldg(&inst->kind) == CRS_INST_MESH) material = __ldg(&sc.spolys[__ldg(sc.slot_poly + tr.best.prim)].material);
+					else material = __ldg(&inst->material);
+					key = material + 1u < 255u ? material + 1u : 255u;
+				}
+				wb.hitKey[ray] = (unsigned char)key;
+				atomicAdd(&s_hist[key], 1u);
 				busy = false;
 			} else {
 				tr.step(sc, &tc);
@@ -82,11 +96,15 @@ __global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int 
 					atomicAdd(&wb.stats[7], 1ull);
 					wb.hit[ray] = make_float4(CR_FLT_MAX, 0.f, 0.f, 0.f);
 					wb.hitInst[ray] = -1;
+					wb.hitKey[ray] = 0;
+					atomicAdd(&s_hist[0], 1u);
 					busy = false;
 				}
 			}
 		}
 	}
+	__syncthreads();
+	if (s_hist[threadIdx.x]) atomicAdd(&wb.hist[threadIdx.x], s_hist[threadIdx.x]);
 	if (COUNT) {
 		atomicAdd(&wb.stats[1], (unsigned long long)tc.pairs);
 		atomicAdd(&wb.stats[2], (unsigned long long)tc.tris);

@@ -7,6 +7,8 @@
  *   K1 k_generate    initSampler + getCameraRay for every path            (sampler.c:41-44, camera.c:58-87)
  *   per bounce:
  *   K2 k_trace       closest hit of every live ray                        (pathtrace.c:38 → bvh.c, poly.c, sphere.c)
+ *   K4 k_bucket      counting sort of the live rays by shading bucket (miss / material id) so that the
+ *                    32 lanes of a K3 warp run the same node graph (K2 fills the histogram)
  *   K3 k_shade       miss → background, hit → emission, bsdf sample, Russian roulette, weight update;
  *                    survivors are COMPACTED into the other half of the ping-pong ray buffers with one
  *                    warp-ballot + one atomicAdd per warp (K4 is fused into K3)   (pathtrace.c:39-57)
@@ -31,6 +33,9 @@ struct WaveBuffers {
 	float4 *hit;
 	int    *hitInst;
 	float4 *L;
+	unsigned char *hitKey;  /* shading bucket of the hit: 0 = miss, else min(material+1, 255) */
+	unsigned *perm;         /* K4 output: live indices grouped by bucket */
+	unsigned *hist;         /* [256] bucket sizes (filled by K2), [256..511] K4 cursors */
 	unsigned *counts;       /* [0],[1]: live counts of the ping-pong halves; [2]: K2's work counter (next ray to hand out) */
 	unsigned long long *stats; /* [0] rays, [1] pairs, [2] tris, [3] spheres, [4] insts */
 };
@@ -43,6 +48,7 @@ struct TileDesc {
 /* launchers (defined in crgpu_trace.cu / crgpu_shade.cu); `dsc` is the device copy of `sc` */
 void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDesc &td, int grid, cudaStream_t st);
 void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, int grid, cudaStream_t st);
+void crg_launch_bucket(const WaveBuffers &wb, int cur, int grid, cudaStream_t st);
 void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int grid, cudaStream_t st);
 void crg_launch_accumulate(float *fb, const float4 *L, const TileDesc &td, int W, int H, int grid, cudaStream_t st);
 void crg_launch_to_srgb8(const float *fb, uint8_t *out, size_t n, int grid, cudaStream_t st);
