@@ -131,7 +131,7 @@ def reference_arm(args, w, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    spp = args.cpu_spp or max(1, min(w["spp"], int(2.0e6 * cores * 1.0 / (w["width"] * w["height"])) or 1))  # ~1 s/step/core-rate guess
+    spp = args.cpu_spp or max(1, min(w["spp"], int(5.0e7 / (w["width"] * w["height"])) or 1))   # a few seconds of CPU rendering per step
     rays_per_sample = float(os.environ.get("CRAY_RAYS_PER_SAMPLE", "0")) or None
     times = []
     for i in range(args.warmup + args.steps):
@@ -339,7 +339,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        cspp = args.cpu_spp or max(1, min(spp, int(8.0e6 * cores * 1.0 / (W * H)) or 1))   # ~10-20 s at ~0.6 Msample/s/core
+        cspp = args.cpu_spp or max(1, min(spp, int(2.5e8 / (W * H)) or 1))   # ~10-30 s of CPU rendering (5-15 Msample/s on the host)
         r = run_reference(w["scene"], W, H, cspp, bounces, cores)
         if r:
             secs, samples, threads = r

@@ -631,6 +631,14 @@ extern "C" int crgpu_framebuffer_device_ptr(crgpu_scene *s, void **dev_ptr, size
 	return CRGPU_OK;
 }
 
+extern "C" int crgpu_scene_info(crgpu_scene *s, int *device, int *width, int *height) {
+	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
+	if (device) *device = s->device;
+	if (width) *width = (int)s->dev.image_width;
+	if (height) *height = (int)s->dev.image_height;
+	return CRGPU_OK;
+}
+
 extern "C" int crgpu_trace_kat(crgpu_scene *s, const int32_t *xyp, int count, void *records_out) {
 	if (!s || !xyp || !records_out || count < 0) return fail(CRGPU_ERR_BAD_ARGUMENT, "bad argument");
 	if (count == 0) return CRGPU_OK;

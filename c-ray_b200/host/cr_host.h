@@ -1,0 +1,114 @@
+/*
+ * cr_host.h — host-side C mirror of c-ray's renderer / tile dispatcher, with GPU worker threads.
+ *
+ * Same names, argument meaning and division of labour as the reference so that the hot path drops in
+ * behind the existing dispatcher:
+ *   struct renderTile          reference src/datatypes/tile.h:28-37
+ *   quantizeImage / nextTile   reference src/datatypes/tile.c:66-117 / :22-45
+ *   struct renderThreadState   reference src/renderer/renderer.h:14-31 (the fields workers publish)
+ *   struct renderer / prefs    reference src/renderer/renderer.h:58-98 (the subset this path needs)
+ *   renderFrame                reference src/renderer/renderer.c:40-180
+ *   gpuRenderThread            occupies the thread-function slot of renderThread (renderer.c:258-327)
+ *   writeImage                 reference src/utils/encoders/encoder.c:22-39 (PNG / BMP, 8-bit sRGB)
+ *
+ * The scene arrives as the flat description of include/crscene.h (what c-ray's loader + BVH builder
+ * produce, flattened); everything the workers compute happens in libcrgpu.so (include/crgpu.h).
+ * Plain C99 + pthreads.  No CPU rendering path exists here.
+ */
+#pragma once
+#include <stdbool.h>
+#include <stdint.h>
+#include <pthread.h>
+#include "../../include/crgpu.h"
+
+struct intCoord { int x, y; };
+
+enum renderOrder {                 /* tile.h:15-21 */
+	renderOrderTopToBottom = 0,
+	renderOrderFromMiddle,
+	renderOrderToMiddle,
+	renderOrderNormal,
+	renderOrderRandom
+};
+
+struct renderTile {                /* tile.h:28-37 */
+	unsigned width, height;
+	struct intCoord begin, end;    /* end exclusive, y up */
+	bool isRendering, renderComplete, networkRenderer;
+	int tileNum;
+};
+
+enum fileType { bmp = 0, png = 1 };
+
+struct texture8 {                  /* the char_p texture renderFrame returns (renderer.c:41) */
+	unsigned width, height;
+	uint8_t *data;                 /* W*H*3, row 0 = image top */
+};
+
+struct renderer;
+
+struct renderThreadState {         /* renderer.h:14-31 */
+	int thread_num;                /* = CUDA device ordinal of this worker */
+	bool threadComplete;
+	bool paused;
+	int currentTileNum;
+	int completedSamples;
+	uint64_t totalSamples;
+	long avgSampleTime;            /* microseconds per tile-pass */
+	struct renderer *renderer;
+	crgpu_scene *gpu;              /* this worker's device-resident scene replica */
+	uint64_t rays;                 /* closest-hit queries traced by this worker */
+	int error;                     /* first CRGPU_ERR_* seen, 0 = none */
+};
+
+struct prefs {                     /* renderer.h:58-87 */
+	enum renderOrder tileOrder;
+	int threadCount;               /* = number of GPU workers */
+	int sampleCount, bounces;
+	unsigned tileWidth, tileHeight;
+	unsigned imageWidth, imageHeight;
+	const char *imgFilePath, *imgFileName;
+	int imgCount;
+	enum fileType imgType;
+	bool quiet;
+};
+
+struct state {                     /* renderer.h:34-55 */
+	struct renderTile *renderTiles;
+	int tileCount, finishedTileCount;
+	int *tileOwner;                /* worker (= device) that rendered each tile, for the multi-GPU gather */
+	float *renderBuffer;           /* fp32 W*H*3, row H-1-y (scene.c:200, texture.c:24-28) */
+	int activeThreads;
+	bool isRendering, renderAborted;
+	pthread_t *threads;
+	struct renderThreadState *threadStates;
+	pthread_mutex_t tileMutex;
+	double renderSeconds;
+	uint64_t totalRays;
+};
+
+struct renderer {
+	struct crs_scene scene;        /* flat scene (owned) */
+	struct state state;
+	struct prefs prefs;
+};
+
+/* tile dispatcher */
+unsigned quantizeImage(struct renderTile **renderTiles, unsigned width, unsigned height,
+					   unsigned tileWidth, unsigned tileHeight, enum renderOrder tileOrder);
+struct renderTile nextTile(struct renderer *r);
+
+/* renderer */
+struct renderer *newRenderer(void);
+int loadSceneFile(struct renderer *r, const char *crscene_path, int width, int height, int samples, int bounces);
+struct texture8 *renderFrame(struct renderer *r);          /* NULL on error */
+void destroyTexture8(struct texture8 *t);
+void destroyRenderer(struct renderer *r);
+
+/* worker entry point with the signature of renderThread (void *(*)(void *)) */
+void *gpuRenderThread(void *arg);
+
+/* encoders: 8-bit RGB, rows top to bottom */
+int writeImage(const struct texture8 *img, const char *path, enum fileType type);
+int encodeBMP(const struct texture8 *img, const char *path);
+int encodePNG(const struct texture8 *img, const char *path);

@@ -1,0 +1,173 @@
+/*
+ * cr_renderer.c — renderFrame and the GPU worker thread.
+ *
+ * renderFrame restates reference src/renderer/renderer.c:40-180: allocate the 8-bit output, start
+ * prefs.threadCount workers through the thread-function slot, poll their renderThreadState every 16 ms
+ * for the progress line, join, return the image.  The workers are gpuRenderThread (one per CUDA device)
+ * instead of renderThread (renderer.c:258-327): same tile queue (nextTile), same published fields, but a
+ * tile's passes are handed to crgpu_render_tile in one call and pixels never touch the CPU.
+ * With more than one GPU the tiles are gathered on device 0 by one NCCL exchange (include/crgpu_nccl.h).
+ */
+#include "cr_host.h"
+#include "../../include/crgpu_nccl.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+static double now_s(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+struct renderer *newRenderer(void) {                              /* renderer.c:329-343 */
+	struct renderer *r = calloc(1, sizeof *r);
+	if (!r) return NULL;
+	pthread_mutex_init(&r->state.tileMutex, NULL);
+	r->prefs.threadCount = 1;
+	r->prefs.imgType = png;
+	r->prefs.imgFilePath = "./";
+	r->prefs.imgFileName = "rendered";
+	return r;
+}
+
+int loadSceneFile(struct renderer *r, const char *path, int width, int height, int samples, int bounces) {
+	/* the part of loadScene (src/datatypes/scene.c:111-213) that follows parsing + BVH build */
+	if (crscene_load(&r->scene, path) != 0) return -1;
+	crscene_set_config(&r->scene, width, height, samples, bounces);
+	r->prefs.imageWidth = r->scene.prefs.image_width;
+	r->prefs.imageHeight = r->scene.prefs.image_height;
+	r->prefs.sampleCount = (int)r->scene.prefs.sample_count;
+	r->prefs.bounces = (int)r->scene.prefs.bounces;
+	if (!r->prefs.tileWidth) r->prefs.tileWidth = r->scene.prefs.tile_width ? r->scene.prefs.tile_width : 64;
+	if (!r->prefs.tileHeight) r->prefs.tileHeight = r->scene.prefs.tile_height ? r->scene.prefs.tile_height : 64;
+	r->prefs.tileOrder = (enum renderOrder)r->scene.prefs.tile_order;
+	free(r->state.renderTiles);
+	r->state.tileCount = (int)quantizeImage(&r->state.renderTiles, r->prefs.imageWidth, r->prefs.imageHeight,
+											r->prefs.tileWidth, r->prefs.tileHeight, r->prefs.tileOrder);   /* scene.c:187-192 */
+	free(r->state.tileOwner);
+	r->state.tileOwner = calloc((size_t)r->state.tileCount + 1, sizeof(int));
+	free(r->state.renderBuffer);
+	r->state.renderBuffer = calloc((size_t)r->prefs.imageWidth * r->prefs.imageHeight * 3, sizeof(float));   /* scene.c:200 */
+	return r->state.renderBuffer && r->state.renderTiles ? 0 : -1;
+}
+
+void *gpuRenderThread(void *arg) {
+	struct renderThreadState *ts = arg;
+	struct renderer *r = ts->renderer;
+	struct renderTile tile = nextTile(r);                         /* renderer.c:265 */
+	ts->currentTileNum = tile.tileNum;
+	while (tile.tileNum != -1 && r->state.isRendering && !r->state.renderAborted) {
+		const double t0 = now_s();
+		struct crgpu_stats st;
+		const int rc = crgpu_render_tile(ts->gpu, tile.begin.x, tile.begin.y, tile.end.x, tile.end.y,
+										 0, r->prefs.sampleCount, 0u, &st);
+		if (rc != CRGPU_OK) {
+			fprintf(stderr, "gpuRenderThread[%d]: %s\n", ts->thread_num, crgpu_last_error());
+			ts->error = rc;
+			r->state.renderAborted = true;
+			break;
+		}
+		ts->rays += st.rays;
+		ts->totalSamples += (uint64_t)r->prefs.sampleCount;       /* passes done, renderer.c:307 */
+		ts->completedSamples = r->prefs.sampleCount;
+		ts->avgSampleTime = (long)(1e6 * (now_s() - t0) / (double)r->prefs.sampleCount);
+		r->state.renderTiles[tile.tileNum].isRendering = false;   /* renderer.c:315-316 */
+		r->state.renderTiles[tile.tileNum].renderComplete = true;
+		r->state.tileOwner[tile.tileNum] = ts->thread_num;
+		ts->currentTileNum = -1;
+		tile = nextTile(r);
+		ts->currentTileNum = tile.tileNum;
+	}
+	ts->threadComplete = true;                                    /* renderer.c:323 */
+	ts->currentTileNum = -1;
+	return NULL;
+}
+
+struct texture8 *renderFrame(struct renderer *r) {
+	const int n = r->prefs.threadCount < 1 ? 1 : r->prefs.threadCount;
+	const unsigned W = r->prefs.imageWidth, H = r->prefs.imageHeight;
+	int ndev = 0;
+	if (crgpu_device_count(&ndev) != CRGPU_OK || ndev < n) {
+		fprintf(stderr, "renderFrame: %d GPU worker(s) requested, %d CUDA device(s) present: %s\n", n, ndev, crgpu_last_error());
+		return NULL;
+	}
+	struct texture8 *output = calloc(1, sizeof *output);          /* renderer.c:41 */
+	output->width = W; output->height = H;
+	output->data = calloc((size_t)W * H * 3, 1);
+	r->state.threads = calloc((size_t)n, sizeof *r->state.threads);
+	r->state.threadStates = calloc((size_t)n, sizeof *r->state.threadStates);
+	crgpu_scene **scenes = calloc((size_t)n, sizeof *scenes);
+	for (int t = 0; t < n; ++t) {                                 /* one scene replica per GPU */
+		if (crgpu_scene_create(&r->scene, t, &scenes[t]) != CRGPU_OK) {
+			fprintf(stderr, "renderFrame: scene upload to device %d failed: %s\n", t, crgpu_last_error());
+			for (int k = 0; k < t; ++k) crgpu_scene_destroy(scenes[k]);
+			free(scenes); destroyTexture8(output);
+			return NULL;
+		}
+	}
+	r->state.isRendering = true;
+	r->state.renderAborted = false;
+	r->state.finishedTileCount = 0;
+	for (int i = 0; i < r->state.tileCount; ++i) r->state.renderTiles[i].renderComplete = false;
+	if (!r->prefs.quiet) printf("Rendering %ux%u, %d samples, %d bounces on %d GPU%s, %d tiles\n", W, H, r->prefs.sampleCount,
+								r->prefs.bounces, n, n > 1 ? "s" : "", r->state.tileCount);
+	const double t0 = now_s();
+	for (int t = 0; t < n; ++t) {                                 /* renderer.c:97-105 */
+		r->state.threadStates[t] = (struct renderThreadState){ .thread_num = t, .renderer = r, .gpu = scenes[t], .currentTileNum = -1 };
+		if (pthread_create(&r->state.threads[t], NULL, gpuRenderThread, &r->state.threadStates[t]) == 0) r->state.activeThreads++;
+	}
+	while (r->state.isRendering) {                                /* renderer.c:122-172 */
+		struct timespec ts = { 0, 16 * 1000 * 1000 };
+		nanosleep(&ts, NULL);
+		int done = 0;
+		for (int t = 0; t < n; ++t) done += r->state.threadStates[t].threadComplete ? 1 : 0;
+		if (done == n) r->state.isRendering = false;
+	}
+	for (int t = 0; t < n; ++t) pthread_join(r->state.threads[t], NULL);   /* renderer.c:175-177 */
+	r->state.activeThreads = 0;
+	int err = 0;
+	r->state.totalRays = 0;
+	for (int t = 0; t < n; ++t) { err |= r->state.threadStates[t].error; r->state.totalRays += r->state.threadStates[t].rays; }
+
+	r->state.renderSeconds = now_s() - t0;
+	if (!err) {
+		if (n > 1) {
+			/* every worker logged which tiles it rendered (state.tileOwner); gather them on device 0 */
+			int *rects = malloc(sizeof(int) * 4 * (size_t)r->state.tileCount);
+			int *owner = malloc(sizeof(int) * (size_t)r->state.tileCount);
+			for (int i = 0; i < r->state.tileCount; ++i) {
+				const struct renderTile *t = &r->state.renderTiles[i];
+				rects[4 * i] = t->begin.x; rects[4 * i + 1] = t->begin.y; rects[4 * i + 2] = t->end.x; rects[4 * i + 3] = t->end.y;
+				owner[i] = r->state.tileOwner[i];
+			}
+			crgpu_comm *comm = NULL;
+			if (crgpu_comm_create(scenes, n, &comm) != CRGPU_OK || crgpu_comm_gather_tiles(comm, rects, owner, r->state.tileCount, 0) != CRGPU_OK) err = CRGPU_ERR_CUDA;
+			crgpu_comm_destroy(comm);
+			free(rects); free(owner);
+		}
+		r->state.renderSeconds = now_s() - t0;
+		if (!err && crgpu_framebuffer_read(scenes[0], r->state.renderBuffer, 0, 0, 0, 0) != CRGPU_OK) err = CRGPU_ERR_CUDA;   /* renderBuffer, scene.c:200 */
+		if (!err && crgpu_framebuffer_to_srgb8(scenes[0], output->data) != CRGPU_OK) err = CRGPU_ERR_CUDA;            /* renderer.c:297-300 */
+	}
+	for (int t = 0; t < n; ++t) crgpu_scene_destroy(scenes[t]);
+	free(scenes);
+	if (!r->prefs.quiet && !err) {
+		const double samples = (double)W * H * r->prefs.sampleCount;
+		printf("Finished render in %.3f s: %.2f Msample/s, %.2f Mray/s (%llu rays)\n", r->state.renderSeconds,
+			   samples / r->state.renderSeconds / 1e6, (double)r->state.totalRays / r->state.renderSeconds / 1e6, (unsigned long long)r->state.totalRays);
+	}
+	if (err) { destroyTexture8(output); return NULL; }
+	return output;
+}
+
+void destroyTexture8(struct texture8 *t) { if (t) { free(t->data); free(t); } }
+
+void destroyRenderer(struct renderer *r) {                       /* renderer.c:346-362 */
+	if (!r) return;
+	crscene_free(&r->scene);
+	free(r->state.renderTiles); free(r->state.tileOwner); free(r->state.renderBuffer); free(r->state.threads); free(r->state.threadStates);
+	pthread_mutex_destroy(&r->state.tileMutex);
+	free(r);
+}

@@ -98,6 +98,8 @@ int crgpu_framebuffer_write(crgpu_scene *s, const float *host_rgb, int x0, int y
 int crgpu_framebuffer_to_srgb8(crgpu_scene *s, uint8_t *host_rgb8);
 /* Raw device pointer of the fp32 framebuffer (for the NCCL gather done by the multi-GPU host). */
 int crgpu_framebuffer_device_ptr(crgpu_scene *s, void **dev_ptr, size_t *bytes);
+/* Device ordinal and image size of a scene (any pointer may be NULL). */
+int crgpu_scene_info(crgpu_scene *s, int *device, int *width, int *height);
 
 /* Known-answer hook used by the parity tests: camera ray → closest hit → bsdf sample for `count`
  * (x, y, pass) triples, in the 160-byte record layout of oracle/ref_harness.c `struct hit_kat`. */
