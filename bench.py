@@ -103,10 +103,6 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def tiles_of(W, H, t):
-    return [(x, y, min(x + t, W), min(y + t, H)) for y in range(0, H, t) for x in range(0, W, t)]
-
-
 def run_reference(scene, W, H, spp, bounces, threads):
     """The unmodified reference (stock flags, pthreads) on the host cores; returns (seconds of renderFrame, samples)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "cray_ref_stock")
@@ -184,6 +180,7 @@ def main():
     import numpy as np
     import torch
     import crgpu
+    import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
@@ -203,7 +200,7 @@ def main():
         raise SystemExit(f"{scene_path} missing: run __graft_entry__.build() in the build container")
     tile = args.tile or (64 if world > 1 else 0)
     g = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
-    rects = tiles_of(W, H, tile)[rank::world] if tile else [(0, 0, W, H)]
+    rects = shard.rank_rects(W, H, tile, rank, world) if tile else [(0, 0, W, H)]
 
     # zero-copy torch view of the device framebuffer (for the NCCL gather)
     ptr, nbytes = g.device_ptr()
@@ -212,34 +209,16 @@ def main():
         __cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f4", "data": (ptr, False), "version": 2}
     fb = torch.as_tensor(_Fb(), device=dev)
 
-    def pack():
-        return torch.cat([fb[H - y1:H - y0, x0:x1].reshape(-1) for (x0, y0, x1, y1) in rects])
-
-    all_rects = [tiles_of(W, H, tile)[r::world] for r in range(world)] if world > 1 else None
-    sizes = [sum((x1 - x0) * (y1 - y0) * 3 for (x0, y0, x1, y1) in rs) for rs in all_rects] if world > 1 else None
-
     def gather_to_rank0():
-        if world == 1:
-            return
-        mine = pack()
-        pad = max(sizes)
-        buf = torch.zeros(pad, device=dev, dtype=torch.float32)
-        buf[:mine.numel()] = mine
-        outs = [torch.empty(pad, device=dev, dtype=torch.float32) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, outs, dst=0)
-        if rank == 0:
-            for r in range(1, world):
-                off = 0
-                for (x0, y0, x1, y1) in all_rects[r]:
-                    n = (x1 - x0) * (y1 - y0) * 3
-                    fb[H - y1:H - y0, x0:x1] = outs[r][off:off + n].view(y1 - y0, x1 - x0, 3)
-                    off += n
+        shard.gather_to_rank0(fb, W, H, tile, rank, world, dist)
 
     def step(flags=0):
         """one complete frame: enqueue everything on torch's current stream, no host sync inside"""
         g.clear()
-        for r in rects:
-            g.render_tile(*r, flags=flags | crgpu.FLAG_ASYNC)
+        if len(rects) == 1:
+            g.render_tile(*rects[0], flags=flags | crgpu.FLAG_ASYNC)
+        else:
+            g.render_tiles(rects, flags=flags | crgpu.FLAG_ASYNC)     # the rank's whole share of the tile grid as one wavefront
         gather_to_rank0()
 
     def barrier():
@@ -314,10 +293,7 @@ def main():
     prof = g.get_stats()
     cspp = min(spp, 8)
     gc = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
-    cnt = None
-    for r in rects:
-        s_ = gc.render_tile(*r, pass_begin=0, pass_count=cspp, flags=crgpu.FLAG_COUNT)
-        cnt = s_ if cnt is None else {k: cnt[k] + s_[k] for k in cnt}
+    cnt = gc.render_tiles(rects, pass_begin=0, pass_count=cspp, flags=crgpu.FLAG_COUNT)
     gc.close()
     P, T, S, I = (cnt[k] / cnt["rays"] for k in ("node_pairs", "tri_tests", "sphere_tests", "inst_visits"))
     b_ray = 64 * P + 80 * T + 128 * I + 16 * S + 72

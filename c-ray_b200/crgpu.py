@@ -69,6 +69,7 @@ def lib():
         L.crgpu_scene_destroy.argtypes = [P]
         L.crgpu_set_max_paths_in_flight.argtypes = [P, C.c_uint64]
         L.crgpu_render_tile.argtypes = [P] + [C.c_int] * 6 + [C.c_uint, C.POINTER(Stats)]
+        L.crgpu_render_tiles.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(Stats)]
         L.crgpu_set_stream.argtypes = [P, P]
         L.crgpu_get_stats.argtypes = [P, C.POINTER(Stats)]
         L.crgpu_framebuffer_clear.argtypes = [P]
@@ -81,7 +82,7 @@ def lib():
         L.crscene_free.argtypes = [C.POINTER(FlatScene)]
         L.crscene_set_config.argtypes = [C.POINTER(FlatScene)] + [C.c_int] * 4
         for f in ("crgpu_device_count", "crgpu_scene_create", "crgpu_scene_destroy", "crgpu_set_max_paths_in_flight",
-                  "crgpu_render_tile", "crgpu_set_stream", "crgpu_get_stats", "crgpu_framebuffer_clear", "crgpu_framebuffer_read", "crgpu_framebuffer_write",
+                  "crgpu_render_tile", "crgpu_render_tiles", "crgpu_set_stream", "crgpu_get_stats", "crgpu_framebuffer_clear", "crgpu_framebuffer_read", "crgpu_framebuffer_write",
                   "crgpu_framebuffer_to_srgb8", "crgpu_framebuffer_device_ptr", "crgpu_trace_kat", "crscene_load",
                   "crscene_set_config"):
             getattr(L, f).restype = C.c_int
@@ -130,6 +131,16 @@ class GpuScene:
             pass_count = self.samples - pass_begin
         _check(lib().crgpu_render_tile(self.handle, x0, y0, x1, y1, pass_begin, pass_count, flags, C.byref(st)),
                "crgpu_render_tile")
+        return None if (flags & FLAG_ASYNC) else st.as_dict()
+
+    def render_tiles(self, rects, pass_begin=0, pass_count=None, flags=0):
+        """Render a union of tiles [(x0, y0, x1, y1), ...] as ONE wavefront."""
+        st = Stats()
+        if pass_count is None:
+            pass_count = self.samples - pass_begin
+        arr = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+        _check(lib().crgpu_render_tiles(self.handle, arr.ctypes.data, len(arr), pass_begin, pass_count, flags, C.byref(st)),
+               "crgpu_render_tiles")
         return None if (flags & FLAG_ASYNC) else st.as_dict()
 
     def set_stream(self, cuda_stream_ptr):

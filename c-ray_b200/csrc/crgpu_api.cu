@@ -58,6 +58,9 @@ struct crgpu_scene {
 	uint64_t cap_paths;        /* capacity of the wavefront buffers */
 	WaveBuffers wb;
 	cudaEvent_t ev[4];
+	uint32_t *pixels;          /* device pixel list of the last crgpu_render_tiles tile set */
+	size_t pixel_cap;
+	std::vector<int> pixel_key;
 };
 
 template <class T>
@@ -227,7 +230,7 @@ extern "C" int crgpu_scene_destroy(crgpu_scene *s) {
 	if (s->own_stream && s->own_stream != s->stream) cudaStreamSynchronize(s->own_stream);
 	for (void *p : s->allocs) cudaFree(p);
 	WaveBuffers &w = s->wb;
-	void *ptrs[] = { w.stA[0], w.stA[1], w.stB[0], w.stB[1], w.stC[0], w.stC[1], w.hit, w.hitInst, w.L, w.hitKey, w.perm, w.hist, w.counts, w.stats, s->fb, s->fb8 };
+	void *ptrs[] = { w.stA[0], w.stA[1], w.stB[0], w.stB[1], w.stC[0], w.stC[1], w.hit, w.hitInst, w.L, w.hitKey, w.perm, w.hist, w.counts, w.stats, s->fb, s->fb8, s->pixels };
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
 	if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -252,6 +255,7 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	crgpu_scene *s = new crgpu_scene();
 	memset(&s->dev, 0, sizeof s->dev);
 	memset(&s->wb, 0, sizeof s->wb);
+	s->pixels = nullptr; s->pixel_cap = 0;
 	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->own_stream = nullptr; s->cap_paths = 0;
 	memset(s->fetched, 0, sizeof s->fetched);
 	s->pend_paths = s->pend_launches = 0; s->pend_trace_ms = s->pend_shade_ms = s->pend_total_ms = 0.f;
@@ -482,22 +486,17 @@ static int check_rect(const crgpu_scene *s, int x0, int y0, int x1, int y1) {
 	return CRGPU_OK;
 }
 
-extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1, int pass_begin, int pass_count,
-								 unsigned flags, struct crgpu_stats *stats) {
-	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
-	int rc = check_rect(s, x0, y0, x1, y1);
-	if (rc) return rc;
+/* the wavefront driver: passes [pass_begin, +pass_count) over a pixel set (a rectangle, or an explicit list) */
+static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, int pass_begin, int pass_count,
+						 unsigned flags, struct crgpu_stats *stats) {
 	if (pass_begin < 0 || pass_count < 0 || (uint64_t)pass_begin + (uint64_t)pass_count > s->dev.sample_count)
 		return fail(CRGPU_ERR_BAD_ARGUMENT, "passes [%d,%d) outside [0,%u)", pass_begin, pass_begin + pass_count, s->dev.sample_count);
-	CU(cudaSetDevice(s->device));
-	const int tw = x1 - x0, th = y1 - y0;
-	const uint64_t tile_pixels = (uint64_t)tw * (uint64_t)th;
-	if (tile_pixels > s->max_paths) return fail(CRGPU_ERR_BAD_ARGUMENT, "tile has %llu pixels > max paths in flight %llu: use smaller tiles or raise the limit",
+	if (tile_pixels > s->max_paths) return fail(CRGPU_ERR_BAD_ARGUMENT, "pixel set has %llu pixels > max paths in flight %llu: use smaller tiles or raise the limit",
 												(unsigned long long)tile_pixels, (unsigned long long)s->max_paths);
 	uint64_t batch = s->max_paths / tile_pixels;
 	if (batch > (uint64_t)pass_count) batch = (uint64_t)pass_count;
 	if (batch < 1) batch = 1;
-	rc = alloc_wave(s, tile_pixels * batch);
+	int rc = alloc_wave(s, tile_pixels * batch);
 	if (rc) return rc;
 
 	cudaStream_t st = s->stream;
@@ -510,8 +509,8 @@ extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 	if (timing) CU(cudaEventRecord(s->ev[0], st));
 	std::vector<cudaEvent_t> tev;   /* per-kernel events when timing */
 	for (int pb = pass_begin; pb < pass_begin + pass_count; pb += (int)batch) {
-		TileDesc td;
-		td.x0 = x0; td.y0 = y0; td.tw = tw; td.th = th;
+		TileDesc td = base;
+		td.npix = (unsigned)tile_pixels;
 		td.pass_begin = pb;
 		td.pass_count = (pass_begin + pass_count - pb) < (int)batch ? (pass_begin + pass_count - pb) : (int)batch;
 		crg_launch_generate(s->dev, s->wb, td, grid, st); ++launches;
@@ -549,6 +548,53 @@ extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 	}
 	if (flags & CRGPU_FLAG_ASYNC) return CRGPU_OK;
 	return crgpu_get_stats(s, stats);
+}
+
+extern "C" int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1, int pass_begin, int pass_count,
+								 unsigned flags, struct crgpu_stats *stats) {
+	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
+	int rc = check_rect(s, x0, y0, x1, y1);
+	if (rc) return rc;
+	CU(cudaSetDevice(s->device));
+	TileDesc td;
+	memset(&td, 0, sizeof td);
+	td.x0 = x0; td.y0 = y0; td.tw = x1 - x0; td.th = y1 - y0;
+	td.pixels = nullptr;
+	return render_pixels(s, td, (uint64_t)td.tw * (uint64_t)td.th, pass_begin, pass_count, flags, stats);
+}
+
+extern "C" int crgpu_render_tiles(crgpu_scene *s, const int *rects, int nrects, int pass_begin, int pass_count,
+								  unsigned flags, struct crgpu_stats *stats) {
+	if (!s || !rects || nrects < 1) return fail(CRGPU_ERR_BAD_ARGUMENT, "bad tile list");
+	if (s->dev.image_width > 65535u || s->dev.image_height > 65535u) return fail(CRGPU_ERR_UNSUPPORTED, "tile lists need image dimensions <= 65535");
+	CU(cudaSetDevice(s->device));
+	uint64_t total = 0;
+	for (int i = 0; i < nrects; ++i) {
+		int rc = check_rect(s, rects[4 * i], rects[4 * i + 1], rects[4 * i + 2], rects[4 * i + 3]);
+		if (rc) return rc;
+		total += (uint64_t)(rects[4 * i + 2] - rects[4 * i]) * (uint64_t)(rects[4 * i + 3] - rects[4 * i + 1]);
+	}
+	std::vector<int> key(rects, rects + 4 * (size_t)nrects);
+	if (key != s->pixel_key) {                         /* rebuild the pixel list only when the tile set changes */
+		std::vector<uint32_t> px;
+		px.reserve((size_t)total);
+		for (int i = 0; i < nrects; ++i)
+			for (int y = rects[4 * i + 1]; y < rects[4 * i + 3]; ++y)
+				for (int x = rects[4 * i]; x < rects[4 * i + 2]; ++x) px.push_back((uint32_t)x | ((uint32_t)y << 16));
+		CU(cudaStreamSynchronize(s->stream));
+		if (s->pixel_cap < px.size()) {
+			if (s->pixels) cudaFree(s->pixels);
+			s->pixels = nullptr; s->pixel_cap = 0;
+			CU(cudaMalloc((void **)&s->pixels, px.size() * sizeof(uint32_t)));
+			s->pixel_cap = px.size();
+		}
+		CU(cudaMemcpy(s->pixels, px.data(), px.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		s->pixel_key.swap(key);
+	}
+	TileDesc td;
+	memset(&td, 0, sizeof td);
+	td.pixels = s->pixels;
+	return render_pixels(s, td, total, pass_begin, pass_count, flags, stats);
 }
 
 extern "C" int crgpu_get_stats(crgpu_scene *s, struct crgpu_stats *stats) {

@@ -123,10 +123,10 @@ __global__ void __launch_bounds__(256) k_shade(const DevScene *__restrict__ scp,
 /* ---- K5 ------------------------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_accumulate(float *__restrict__ fb, const float4 *__restrict__ L, TileDesc td,
 													 int image_width, int image_height) {
-	const unsigned tile_pixels = (unsigned)(td.tw * td.th);
+	const unsigned tile_pixels = td.npix;
 	for (unsigned px = blockIdx.x * blockDim.x + threadIdx.x; px < tile_pixels; px += gridDim.x * blockDim.x) {
-		const int x = td.x0 + (int)(px % (unsigned)td.tw);
-		const int y = td.y0 + (int)(px / (unsigned)td.tw);
+		int x, y;
+		crg_pixel_xy(td, px, x, y);
 		float *dst = fb + ((size_t)x + (size_t)(image_height - (y + 1)) * (size_t)image_width) * 3u;  /* texture.c:24-28 */
 		float r = dst[0], g = dst[1], b = dst[2];
 		for (int pl = 0; pl < td.pass_count; ++pl) {

@@ -8,12 +8,12 @@
 
 /* ---- K1 ------------------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, TileDesc td) {
-	const unsigned tile_pixels = (unsigned)(td.tw * td.th);
+	const unsigned tile_pixels = td.npix;
 	const unsigned n = tile_pixels * (unsigned)td.pass_count;
 	for (unsigned id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
 		const unsigned pl = id / tile_pixels, px = id - pl * tile_pixels;
-		const int x = td.x0 + (int)(px % (unsigned)td.tw);
-		const int y = td.y0 + (int)(px / (unsigned)td.tw);
+		int x, y;
+		crg_pixel_xy(td, px, x, y);
 		const uint32_t pixIdx = (uint32_t)(y * (int)sc.image_width + x);                        /* renderer.c:280 */
 		uint64_t rng = cr_rng_init(pixIdx, (uint32_t)(td.pass_begin + (int)pl), sc.sample_count);
 		v3 o, d;

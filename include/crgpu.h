@@ -81,6 +81,11 @@ int crgpu_set_max_paths_in_flight(crgpu_scene *s, uint64_t max_paths);
 int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 					  int pass_begin, int pass_count, unsigned flags, struct crgpu_stats *stats);
 
+/* Same, over a UNION of tiles in one wavefront (rects = 4 ints per tile: x0, y0, x1, y1).  This is how a
+ * rank of a multi-GPU job renders its share of the tile grid without paying the per-tile launch tails. */
+int crgpu_render_tiles(crgpu_scene *s, const int *rects, int nrects,
+					   int pass_begin, int pass_count, unsigned flags, struct crgpu_stats *stats);
+
 /* Run on a caller-owned CUDA stream (a `cudaStream_t` passed as void*; NULL restores the scene's own
  * stream).  Lets a host that already has a stream (e.g. the one its NCCL collectives use) order the
  * kernels with its own work and time them with its own events. */

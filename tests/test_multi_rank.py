@@ -1,0 +1,72 @@
+"""CPU test of the N>1 path: world_size-2 gloo processes shard the tile grid, "render" their tiles with the
+CPU oracle (test infrastructure standing in for the GPU), and the SAME gather code bench.py uses on NCCL
+(c-ray_b200/shard.py) must reassemble a frame bit-identical to a single-rank render."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT, GOLDEN
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(sys.argv[1], "c-ray_b200")); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import shard, oracle_lib as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+sc = O.OracleScene(sys.argv[2])
+W, H, tile = sc.W, sc.H, 16
+fb = np.zeros((H, W, 3), dtype=np.float32)
+for r in shard.rank_rects(W, H, tile, rank, world):
+    sc.render(threads=1, tile=r, rgb=fb)
+t = torch.from_numpy(fb)
+shard.gather_to_rank0(t, W, H, tile, rank, world, dist)
+if rank == 0:
+    t.numpy().tofile(sys.argv[3])
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_ranks_reassemble_the_frame(tmp_path):
+    scene = os.path.join(GOLDEN, "g_nodes.crscene")
+    out = str(tmp_path / "frame.f32")
+    w = tmp_path / "worker.py"
+    w.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), str(w), ROOT, scene, out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    got = np.fromfile(out, dtype=np.float32)
+    ref = np.fromfile(os.path.join(GOLDEN, "g_nodes.f32"), dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_shard_helpers():
+    sys.path.insert(0, os.path.join(ROOT, "c-ray_b200"))
+    import torch
+    import shard
+    W, H, t = 50, 35, 16
+    rects = shard.tiles_of(W, H, t)
+    assert len(rects) == 4 * 3
+    for world in (1, 2, 3, 8):
+        parts = [shard.rank_rects(W, H, t, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == sorted(rects)
+    fb = torch.arange(H * W * 3, dtype=torch.float32).view(H, W, 3)
+    flat = shard.pack(fb, rects[::2])
+    fb2 = torch.zeros_like(fb)
+    shard.unpack_into(fb2, rects[::2], flat)
+    for r in rects[::2]:
+        assert torch.equal(shard.rect_view(fb2, r), shard.rect_view(fb, r))
+    assert shard.rect_view(fb, (0, 0, 16, 16)).shape == (16, 16, 3) and shard.rect_view(fb, (48, 32, 50, 35)).shape == (3, 2, 3)
