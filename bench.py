@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--bounces", type=int, default=0)
-    ap.add_argument("--tile", type=int, default=0, help="tile edge for sharding (0 = auto)")
+    ap.add_argument("--tile", type=int, default=-1, help="tile edge of the tile grid (default 64, the scene's own tile size; 0 = one whole-frame rectangle)")
     ap.add_argument("--max-paths", type=int, default=0, help="paths in flight per wavefront batch (0 = library default)")
     ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
         sm = sorted(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][2]) if self.samples[0][2].replace(".", "").isdigit() else None,
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_mhz_min": sm[0] if sm else None, "sm_max_mhz": float(self.samples[0][2]) if self.samples[0][2].replace(".", "").isdigit() else None,
                 "reasons": reasons, "samples": len(self.samples)}
 
 
@@ -198,7 +198,7 @@ def main():
     scene_path = os.path.join(ROOT, "scenes", "_built", w["scene"] + ".crscene")
     if not os.path.exists(scene_path):
         raise SystemExit(f"{scene_path} missing: run __graft_entry__.build() in the build container")
-    tile = args.tile or (64 if world > 1 else 0)
+    tile = args.tile if args.tile >= 0 else 64      # tile-ordered pixel lists keep warps on compact 2D footprints (faster than row-major)
     g = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
     rects = shard.rank_rects(W, H, tile, rank, world) if tile else [(0, 0, W, H)]
 

@@ -259,7 +259,7 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->own_stream = nullptr; s->cap_paths = 0;
 	memset(s->fetched, 0, sizeof s->fetched);
 	s->pend_paths = s->pend_launches = 0; s->pend_trace_ms = s->pend_shade_ms = s->pend_total_ms = 0.f;
-	s->max_paths = 8ull << 20;
+	s->max_paths = 0;   /* set below from the free device memory */
 	for (auto &e : s->ev) e = nullptr;
 #define FAIL_IF(x) do { int rc_ = (x); if (rc_) { crgpu_scene_destroy(s); return rc_; } } while (0)
 #define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(CRGPU_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); crgpu_scene_destroy(s); return rc_; } } while (0)
@@ -466,6 +466,17 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	CUS(cudaMemset(s->wb.counts, 0, 4 * sizeof(unsigned)));
 	CUS(cudaMalloc((void **)&s->wb.stats, 80 * sizeof(unsigned long long)));
 	CUS(cudaMemset(s->wb.stats, 0, 80 * sizeof(unsigned long long)));
+	{
+		/* Paths in flight per wavefront batch.  Every batch pays a fixed ~7 ms (the serial chain of its bounces: each
+		 * late bounce lasts as long as its slowest ray), so batches should be as large as memory allows:
+		 * 137 B of wavefront state per path; use at most 40% of the free HBM, capped at 256M paths (35 GB). */
+		size_t free_b = 0, total_b = 0;
+		CUS(cudaMemGetInfo(&free_b, &total_b));
+		uint64_t fit = (uint64_t)((double)free_b * 0.40 / 137.0);
+		if (fit > (256ull << 20)) fit = 256ull << 20;
+		if (fit < (1ull << 20)) fit = 1ull << 20;
+		s->max_paths = fit;
+	}
 	CUS(cudaDeviceSynchronize());
 #undef FAIL_IF
 #undef CUS

@@ -5,6 +5,7 @@
  */
 #include "crgpu_wave.cuh"
 #include "crgpu_trace.cuh"
+#include <cstdlib>
 
 /* ---- K1 ------------------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, TileDesc td) {
@@ -34,10 +35,11 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
  * rays for the idle lanes from a global work counter (one ballot + one atomicAdd per refill, indices handed
  * out in lane order so neighbouring lanes still get neighbouring — coherent — rays). */
 #define CRG_REFILL 24
+#define CRG_NODE_BURST 4
 #define CRG_MAX_STEPS 8000000u   /* > 30x the node count of any scene that fits the 2^23-node address space we support */
 
-template <bool COUNT>
-__global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int cur) {
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb, int cur, int refill, int burst) {
 	const unsigned n = wb.counts[cur];
 	const unsigned lane = threadIdx.x & 31u;
 	const float4 *__restrict__ stA = wb.stA[cur];
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int 
 	unsigned steps = 0u;             /* safety net: a lane that exceeds CRG_MAX_STEPS is abandoned and flagged */
 	while (true) {
 		unsigned active = __ballot_sync(0xffffffffu, busy);
-		if (!exhausted && __popc(active) < CRG_REFILL) {
+		if (!exhausted && __popc(active) < refill) {
 			const unsigned idle = ~active;
 			const unsigned nidle = (unsigned)__popc(idle);
 			unsigned base = 0u;
@@ -75,32 +77,39 @@ __global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int 
 			active = __ballot_sync(0xffffffffu, busy);
 		}
 		if (active == 0u) break;         /* nothing in flight and nothing left to fetch */
-		if (busy) {
-			if (tr.done()) {
-				wb.hit[ray] = make_float4(tr.best.t, tr.best.u, tr.best.v, __uint_as_float(tr.best.prim));
-				wb.hitInst[ray] = tr.best.inst;
-				unsigned key = 0u;                                   /* shading bucket for K4/K3 */
-				if (tr.best.inst >= 0) {
-					const DevInstance *inst = sc.instances + tr.best.inst;
-					unsigned material;
-					if (__ldg(&inst->kind) == CRS_INST_MESH) material = __ldg(&sc.spolys[__ldg(sc.slot_poly + tr.best.prim)].material);
-					else material = __ldg(&inst->material);
-					key = material + 1u < 255u ? material + 1u : 255u;
-				}
-				wb.hitKey[ray] = (unsigned char)key;
-				atomicAdd(&s_hist[key], 1u);
-				busy = false;
-			} else {
-				tr.step(sc, &tc);
-				if (++steps > CRG_MAX_STEPS) {   /* cannot happen for a finite BVH; never hang the GPU */
-					atomicAdd(&wb.stats[7], 1ull);
-					wb.hit[ray] = make_float4(CR_FLT_MAX, 0.f, 0.f, 0.f);
-					wb.hitInst[ray] = -1;
-					wb.hitKey[ray] = 0;
-					atomicAdd(&s_hist[0], 1u);
-					busy = false;
-				}
+		/* Phase N: up to CRG_NODE_BURST child-pair steps for every lane that is inside a BVH.  Lanes that reach a
+		 * top-level leaf (instance work) or finish wait here, so that the instance / write-back code below runs
+		 * for many lanes at once instead of being serialised against node steps in every iteration. */
+#pragma unroll 1
+		for (int k = 0; k < burst; ++k) {
+			const bool wn = busy && tr.wants_node();
+			if (!__any_sync(0xffffffffu, wn)) break;
+			if (wn) { tr.node_step(sc, &tc); ++steps; }
+		}
+		/* Phase I: one pending instance (ray transform + sphere test, or entry into a mesh BVH) */
+		if (busy && tr.wants_instance()) { tr.instance_step(sc, &tc); ++steps; }
+		/* Phase W: write back finished rays */
+		if (busy && tr.done()) {
+			wb.hit[ray] = make_float4(tr.best.t, tr.best.u, tr.best.v, __uint_as_float(tr.best.prim));
+			wb.hitInst[ray] = tr.best.inst;
+			unsigned key = 0u;                                   /* shading bucket for K4/K3 */
+			if (tr.best.inst >= 0) {
+				const DevInstance *inst = sc.instances + tr.best.inst;
+				unsigned material;
+				if (__ldg(&inst->kind) == CRS_INST_MESH) material = __ldg(&sc.spolys[__ldg(sc.slot_poly + tr.best.prim)].material);
+				else material = __ldg(&inst->material);
+				key = material + 1u < 255u ? material + 1u : 255u;
 			}
+			wb.hitKey[ray] = (unsigned char)key;
+			atomicAdd(&s_hist[key], 1u);
+			busy = false;
+		} else if (busy && steps > CRG_MAX_STEPS) {              /* cannot happen for a finite BVH; never hang the GPU */
+			atomicAdd(&wb.stats[7], 1ull);
+			wb.hit[ray] = make_float4(CR_FLT_MAX, 0.f, 0.f, 0.f);
+			wb.hitInst[ray] = -1;
+			wb.hitKey[ray] = 0;
+			atomicAdd(&s_hist[0], 1u);
+			busy = false;
 		}
 	}
 	__syncthreads();
@@ -120,7 +129,31 @@ __global__ void __launch_bounds__(256) k_trace(DevScene sc, WaveBuffers wb, int 
 void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDesc &td, int grid, cudaStream_t st) {
 	k_generate<<<grid, 256, 0, st>>>(sc, wb, td);
 }
+/* K2 is persistent: the grid is exactly the number of blocks the device can keep resident.  MINB (blocks per SM
+ * the compiler must make room for: 2 -> <=128 registers, 3 -> <=80, 4 -> <=64) trades registers for latency-hiding warps;
+ * CRGPU_TRACE_MINB=2|3 overrides the default for experiments. */
+template <bool COUNT, int MINB>
+static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int cur, cudaStream_t st) {
+	static int grid = 0;
+	if (!grid) {
+		int dev = 0, sms = 0, occ = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<COUNT, MINB>, 256, 0);
+		grid = sms * (occ > 0 ? occ : 1);
+	}
+	static int refill = 0, burst = 0;
+	if (!refill) { const char *e = getenv("CRGPU_TRACE_REFILL"); refill = e ? atoi(e) : CRG_REFILL; if (refill < 1 || refill > 32) refill = CRG_REFILL;
+		e = getenv("CRGPU_TRACE_BURST"); burst = e ? atoi(e) : CRG_NODE_BURST; if (burst < 1) burst = CRG_NODE_BURST; }
+	k_trace<COUNT, MINB><<<grid, 256, 0, st>>>(sc, wb, cur, refill, burst);
+}
+
 void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, int grid, cudaStream_t st) {
-	if (count) k_trace<true><<<grid, 256, 0, st>>>(sc, wb, cur);
-	else k_trace<false><<<grid, 256, 0, st>>>(sc, wb, cur);
+	(void)grid;
+	static int minb = 0;
+	if (!minb) { const char *e = getenv("CRGPU_TRACE_MINB"); minb = e ? atoi(e) : 3; if (minb < 2 || minb > 4) minb = 3; }
+	if (count) { launch_trace_variant<true, 3>(sc, wb, cur, st); return; }
+	if (minb == 4) launch_trace_variant<false, 4>(sc, wb, cur, st);
+	else if (minb == 2) launch_trace_variant<false, 2>(sc, wb, cur, st);
+	else launch_trace_variant<false, 3>(sc, wb, cur, st);
 }

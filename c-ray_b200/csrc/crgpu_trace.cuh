@@ -214,9 +214,18 @@ struct Traversal {
 		}
 	}
 
+	CRD bool wants_node() const { return bottom || ((cntA | cntB) == 0u && node != CRG_END); }
+	CRD bool wants_instance() const { return !bottom && (cntA | cntB) != 0u; }
+
 	/* one iteration of the flat loop; precondition: !done() */
 	CRD void step(const DevScene &sc, TraceCounters *ctr) {
-		if (bottom || (cntA | cntB) == 0u) {
+		if (bottom || (cntA | cntB) == 0u) node_step(sc, ctr);
+		else instance_step(sc, ctr);
+	}
+
+	/* precondition: wants_node() */
+	CRD void node_step(const DevScene &sc, TraceCounters *ctr) {
+		{
 			/* ---- one child-pair step (bvh.c:391-439) */
 			const float4 *p4 = reinterpret_cast<const float4 *>(base + node);
 			const float4 q0 = __ldg(p4 + 0), q1 = __ldg(p4 + 1), q2 = __ldg(p4 + 2);
@@ -257,7 +266,12 @@ struct Traversal {
 				if (hitR && leafR) { pendB = q3.y; cntB = q3.w & ~CRG_LEAF_BIT; }
 				node = next;
 			}
-		} else {
+		}
+	}
+
+	/* precondition: wants_instance() */
+	CRD void instance_step(const DevScene &sc, TraceCounters *ctr) {
+		{
 			/* ---- one instance of a pending top-level leaf (bvh.c:468-486) */
 			uint32_t idx;
 			if (cntA) { idx = pendA++; --cntA; } else { idx = pendB++; --cntB; }

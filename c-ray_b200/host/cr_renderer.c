@@ -53,16 +53,39 @@ int loadSceneFile(struct renderer *r, const char *path, int width, int height, i
 	return r->state.renderBuffer && r->state.renderTiles ? 0 : -1;
 }
 
+/* How many tiles a GPU worker takes from the queue per trip.  A CPU thread takes one (renderer.c:265,318); a GPU
+ * wavefront pays a fixed ~7 ms latency chain per batch, so a worker takes enough tiles to put ~64M paths in flight,
+ * but never more than its fair share of what is left (keeps several GPUs balanced). */
+static int tiles_per_trip(const struct renderer *r) {
+	const double tilePaths = (double)r->prefs.tileWidth * r->prefs.tileHeight * (double)r->prefs.sampleCount;
+	int want = (int)(64.0 * 1048576.0 / (tilePaths > 1.0 ? tilePaths : 1.0)) + 1;
+	const int left = r->state.tileCount - r->state.finishedTileCount;
+	const int share = (left + r->prefs.threadCount - 1) / (r->prefs.threadCount > 0 ? r->prefs.threadCount : 1);
+	if (want > share) want = share;
+	if (want > 1024) want = 1024;
+	return want < 1 ? 1 : want;
+}
+
 void *gpuRenderThread(void *arg) {
 	struct renderThreadState *ts = arg;
 	struct renderer *r = ts->renderer;
-	struct renderTile tile = nextTile(r);                         /* renderer.c:265 */
-	ts->currentTileNum = tile.tileNum;
-	while (tile.tileNum != -1 && r->state.isRendering && !r->state.renderAborted) {
+	int *rects = malloc(sizeof(int) * 4 * 1024);
+	int *nums = malloc(sizeof(int) * 1024);
+	while (r->state.isRendering && !r->state.renderAborted) {
+		/* take a handful of tiles from the shared queue (nextTile, tile.c:22-45) */
+		const int want = tiles_per_trip(r);
+		int got = 0;
+		while (got < want) {
+			struct renderTile tile = nextTile(r);
+			if (tile.tileNum == -1) break;
+			rects[4 * got] = tile.begin.x; rects[4 * got + 1] = tile.begin.y; rects[4 * got + 2] = tile.end.x; rects[4 * got + 3] = tile.end.y;
+			nums[got++] = tile.tileNum;
+		}
+		if (got == 0) break;
+		ts->currentTileNum = nums[0];
 		const double t0 = now_s();
 		struct crgpu_stats st;
-		const int rc = crgpu_render_tile(ts->gpu, tile.begin.x, tile.begin.y, tile.end.x, tile.end.y,
-										 0, r->prefs.sampleCount, 0u, &st);
+		const int rc = crgpu_render_tiles(ts->gpu, rects, got, 0, r->prefs.sampleCount, 0u, &st);
 		if (rc != CRGPU_OK) {
 			fprintf(stderr, "gpuRenderThread[%d]: %s\n", ts->thread_num, crgpu_last_error());
 			ts->error = rc;
@@ -70,16 +93,17 @@ void *gpuRenderThread(void *arg) {
 			break;
 		}
 		ts->rays += st.rays;
-		ts->totalSamples += (uint64_t)r->prefs.sampleCount;       /* passes done, renderer.c:307 */
+		ts->totalSamples += (uint64_t)r->prefs.sampleCount * (uint64_t)got;      /* tile-passes done, renderer.c:307 */
 		ts->completedSamples = r->prefs.sampleCount;
-		ts->avgSampleTime = (long)(1e6 * (now_s() - t0) / (double)r->prefs.sampleCount);
-		r->state.renderTiles[tile.tileNum].isRendering = false;   /* renderer.c:315-316 */
-		r->state.renderTiles[tile.tileNum].renderComplete = true;
-		r->state.tileOwner[tile.tileNum] = ts->thread_num;
+		ts->avgSampleTime = (long)(1e6 * (now_s() - t0) / ((double)r->prefs.sampleCount * got));
+		for (int i = 0; i < got; ++i) {
+			r->state.renderTiles[nums[i]].isRendering = false;                    /* renderer.c:315-316 */
+			r->state.renderTiles[nums[i]].renderComplete = true;
+			r->state.tileOwner[nums[i]] = ts->thread_num;
+		}
 		ts->currentTileNum = -1;
-		tile = nextTile(r);
-		ts->currentTileNum = tile.tileNum;
 	}
+	free(rects); free(nums);
 	ts->threadComplete = true;                                    /* renderer.c:323 */
 	ts->currentTileNum = -1;
 	return NULL;

@@ -69,8 +69,9 @@ const char *crgpu_last_error(void);
 int crgpu_scene_create(const struct crs_scene *flat, int device, crgpu_scene **out);
 int crgpu_scene_destroy(crgpu_scene *s);
 
-/* Limit on paths in flight per wavefront batch (default 8M); the tile's passes are processed in
- * batches of floor(max_paths / tile_pixels) passes.  Results do not depend on it. */
+/* Limit on paths in flight per wavefront batch (default: what fits in 40% of the free device memory at
+ * 137 B per path, at most 256M); a tile's passes are processed in batches of floor(max_paths / tile_pixels)
+ * passes.  Results do not depend on it; throughput does (every batch pays a fixed latency chain). */
 int crgpu_set_max_paths_in_flight(crgpu_scene *s, uint64_t max_paths);
 
 /* Render passes [pass_begin, pass_begin+pass_count) of the tile [x0,x1) x [y0,y1) (y up, end

@@ -1,5 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
-timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>&1; echo "ref rc=$?"; tail -c 1500 gpurun_out/bench_ref.json
-nproc; lscpu | grep "Model name"
+run() { # name envs...
+  env "$@" timeout 200 python bench.py --workload ${WL:-hdr} --spp 256 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bq.json 2>gpurun_out/bq.err; python -c "
+import json;d=json.load(open('gpurun_out/bq.json'));print('$* ${WL:-hdr}', d['value'], d['ms_per_step'], d['roofline']['trace_gray_per_s'], d['roofline']['trace_share_of_step'])"; tail -1 gpurun_out/bq.err; }
+run CRGPU_TRACE_BURST=1 CRGPU_TRACE_REFILL=16
+run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=16
+run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=8
+run CRGPU_TRACE_BURST=1 CRGPU_TRACE_REFILL=8
+run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=12
+run CRGPU_TRACE_BURST=3 CRGPU_TRACE_REFILL=16
+WL=venus run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=16
+WL=venus run CRGPU_TRACE_BURST=4 CRGPU_TRACE_REFILL=24
+WL=venus run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=8
