@@ -72,35 +72,42 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons DURING the timed region, read through NVML in-process (spawning nvidia-smi
+    every 200 ms measurably stalls kernel submission: it takes the driver lock for ~0.5 s per call)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.sm, self.mask, self.stop_flag, self.max_mhz, self.err = index, [], 0, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:   # noqa: BLE001
+            self.nv, self.err = None, str(e)
 
     def run(self):
+        if not self.nv:
+            return
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                f = [x.strip() for x in out.split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.2)
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception as e:   # noqa: BLE001
+                self.err = str(e)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_mhz_min": sm[0] if sm else None, "sm_max_mhz": float(self.samples[0][2]) if self.samples[0][2].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable: %s" % self.err]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, bit in self.REASONS.items() if self.mask & bit], "samples": len(sm)}
 
 
 def run_reference(scene, W, H, spp, bounces, threads):
@@ -193,6 +200,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    work_stream = torch.cuda.Stream(device=dev)      # library kernels, NCCL gather and the timing events all live on this stream
+    torch.cuda.set_stream(work_stream)
 
     W, H, spp, bounces = w["width"], w["height"], w["spp"], w["bounces"]
     scene_path = os.path.join(ROOT, "scenes", "_built", w["scene"] + ".crscene")
@@ -236,12 +245,24 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # the library enqueues on torch's current stream (crgpu_set_stream), so these events bracket exactly its kernels
+    step_evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] if os.environ.get("CRAY_BENCH_STEP_TIMES") else None
+    wall0 = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        if step_evs:
+            step_evs[i].record()
         step()
+    if step_evs:
+        step_evs[-1].record()
     ev1.record()
     barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
     ms = ev0.elapsed_time(ev1)
+    if ms < 0.9 * wall_ms:      # events that do not bracket the kernels (wrong stream) must never flatter the number
+        sys.stderr.write(f"bench.py: CUDA-event time {ms:.1f} ms << wall {wall_ms:.1f} ms; reporting wall clock\n")
+        ms = wall_ms
+    if step_evs and rank == 0:
+        sys.stderr.write("per-step ms: %s\n" % [round(step_evs[i].elapsed_time(step_evs[i + 1]), 1) for i in range(args.steps)])
     stats = g.get_stats()
     clocks = sampler.summary()
     tms = torch.tensor([ms, float(stats["rays"]), float(stats["paths"]), float(stats["kernel_launches"])], device=dev, dtype=torch.float64)
@@ -300,9 +321,20 @@ def main():
     peak, peak_kind = peaks()
     trace_s = prof["trace_ms"] / 1e3
     achieved = (prof["rays"] * b_ray / trace_s / 1e9) if trace_s > 0 else None
+    traffic, traffic_note = None, None
+    try:   # DRAM bytes of one K2 launch from the committed ncu --set full capture (not live: ncu replays kernels ~40x)
+        import glob
+        mfile = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_metrics.json")))[-1]
+        m = json.load(open(mfile))["kernels"]["k_trace"][0]
+        traffic = int((m["dram_read"] + m["dram_write"]) * 1e9)
+        traffic_note = (f"{os.path.basename(mfile)}: k_trace bounce-1 launch of a 66M-path batch on input/hdr.json (~40M rays, {m['duration']:.2f} ms): "
+                        f"{traffic / 1e9:.2f} GB of DRAM traffic = ~80 B/ray (the 52-B ray/hit records + misses), far BELOW the 769 B/ray algorithmic "
+                        "figure because nodes and triangles are served by L1/L2")
+    except Exception:   # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 2) if achieved else None, "peak": peak,
                 "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": None,
+                "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
                 "bytes_per_ray": round(b_ray, 1), "per_ray": {"P": round(P, 3), "T": round(T, 3), "I": round(I, 3), "S": round(S, 3)},
                 "trace_share_of_step": round(prof["trace_ms"] / prof["total_ms"], 4) if prof["total_ms"] else None,
                 "shade_share_of_step": round(prof["shade_ms"] / prof["total_ms"], 4) if prof["total_ms"] else None,

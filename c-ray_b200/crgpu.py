@@ -72,6 +72,7 @@ def lib():
         L.crgpu_render_tiles.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(Stats)]
         L.crgpu_set_stream.argtypes = [P, P]
         L.crgpu_get_stats.argtypes = [P, C.POINTER(Stats)]
+        L.crgpu_use_own_stream.argtypes = [P]
         L.crgpu_framebuffer_clear.argtypes = [P]
         L.crgpu_framebuffer_read.argtypes = [P, P] + [C.c_int] * 4
         L.crgpu_framebuffer_write.argtypes = [P, P] + [C.c_int] * 4
@@ -82,7 +83,7 @@ def lib():
         L.crscene_free.argtypes = [C.POINTER(FlatScene)]
         L.crscene_set_config.argtypes = [C.POINTER(FlatScene)] + [C.c_int] * 4
         for f in ("crgpu_device_count", "crgpu_scene_create", "crgpu_scene_destroy", "crgpu_set_max_paths_in_flight",
-                  "crgpu_render_tile", "crgpu_render_tiles", "crgpu_set_stream", "crgpu_get_stats", "crgpu_framebuffer_clear", "crgpu_framebuffer_read", "crgpu_framebuffer_write",
+                  "crgpu_render_tile", "crgpu_render_tiles", "crgpu_set_stream", "crgpu_use_own_stream", "crgpu_get_stats", "crgpu_framebuffer_clear", "crgpu_framebuffer_read", "crgpu_framebuffer_write",
                   "crgpu_framebuffer_to_srgb8", "crgpu_framebuffer_device_ptr", "crgpu_trace_kat", "crscene_load",
                   "crscene_set_config"):
             getattr(L, f).restype = C.c_int

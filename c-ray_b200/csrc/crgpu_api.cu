@@ -157,6 +157,7 @@ static int check_bsdf(const crs_scene *f, int idx, int add_level, int guard, boo
 static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNode> &pairs, DevBvh &out, uint32_t slot_offset) {
 	memset(&out, 0, sizeof out);
 	out.pair_offset = (uint32_t)pairs.size();
+	out.pair_end = out.pair_offset;
 	out.node_count = b.node_count;
 	out.slot_offset = slot_offset;
 	if (b.node_count == 0) return CRGPU_OK;
@@ -200,6 +201,7 @@ static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNod
 		else { p.rref = rank[fc + 1]; p.rmeta = 0; }
 		pairs.push_back(p);
 	}
+	out.pair_end = (uint32_t)pairs.size();
 	return CRGPU_OK;
 }
 
@@ -438,6 +440,35 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	d.background = f->background;
 	d.instance_count = f->instance_count;
 	d.top = bvhs[f->top_bvh];
+	/* staging image: top-of-tree pair nodes (BFS prefix) of every BVH, the top level first, then the meshes
+	 * in proportion to their size, CRG_STAGE_PAIRS nodes in total */
+	std::vector<PairNode> stage;
+	{
+		auto take = [&](DevBvh &b, uint32_t quota) {
+			const uint32_t internal = b.node_count > 1 ? (uint32_t)(b.pair_end - b.pair_offset) : 0u;
+			const uint32_t cnt = quota < internal ? quota : internal;
+			b.stage_base = (uint32_t)stage.size();
+			b.stage_count = cnt;
+			stage.insert(stage.end(), pairs.begin() + b.pair_offset, pairs.begin() + b.pair_offset + cnt);
+		};
+		/* shared memory and L1 share 228 KB per SM: every staged KB is a KB of L1 the traversal loses, so the default
+		 * stages only the very top (128 nodes = 8 KB); CRGPU_TRACE_STAGE=<pairs> (0..1024) overrides */
+		const char *env = getenv("CRGPU_TRACE_STAGE");
+		uint32_t total_budget = env ? (uint32_t)atoi(env) : 128u;
+		if (total_budget > CRG_STAGE_PAIRS) total_budget = CRG_STAGE_PAIRS;
+		take(bvhs[f->top_bvh], total_budget / 4);
+		uint64_t total_internal = 0;
+		for (uint32_t b = 0; b < f->bvh_count; ++b) if (b != f->top_bvh && bvhs[b].node_count > 1) total_internal += bvhs[b].pair_end - bvhs[b].pair_offset;
+		const uint32_t budget = total_budget > (uint32_t)stage.size() ? total_budget - (uint32_t)stage.size() : 0u;
+		for (uint32_t b = 0; b < f->bvh_count && total_internal; ++b) {
+			if (b == f->top_bvh) continue;
+			const uint64_t internal = bvhs[b].node_count > 1 ? bvhs[b].pair_end - bvhs[b].pair_offset : 0;
+			take(bvhs[b], (uint32_t)((uint64_t)budget * internal / total_internal));
+		}
+		d.top = bvhs[f->top_bvh];
+	}
+	d.stage_pairs = (uint32_t)stage.size();
+	FAIL_IF(upload(s, stage, &d.stage_img));
 	FAIL_IF(upload(s, pairs, &d.pairs));
 	FAIL_IF(upload(s, tris, &d.tris));
 	FAIL_IF(upload(s, slot_poly, &d.slot_poly));
@@ -635,7 +666,15 @@ extern "C" int crgpu_set_stream(crgpu_scene *s, void *cuda_stream) {
 	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
 	CU(cudaSetDevice(s->device));
 	CU(cudaStreamSynchronize(s->stream));
-	s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->own_stream;
+	s->stream = static_cast<cudaStream_t>(cuda_stream);      /* NULL is a valid handle: the legacy default stream */
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_use_own_stream(crgpu_scene *s) {
+	if (!s) return fail(CRGPU_ERR_BAD_ARGUMENT, "scene is NULL");
+	CU(cudaSetDevice(s->device));
+	CU(cudaStreamSynchronize(s->stream));
+	s->stream = s->own_stream;
 	return CRGPU_OK;
 }
 

@@ -22,6 +22,7 @@
 
 #define CRG_LEAF_BIT 0x80000000u
 #define CRG_MAX_STACK 64            /* MAX_BVH_DEPTH, bvh.c:32 */
+#define CRG_STAGE_PAIRS 1024         /* 64 KB of shared memory per block for the staged top-of-tree nodes */
 
 struct __align__(64) PairNode {
 	float lb[6];                    /* left child: minx,maxx,miny,maxy,minz,maxz */
@@ -44,10 +45,13 @@ struct __align__(16) ShadePoly {
 
 struct DevBvh {
 	uint32_t pair_offset;           /* into pairs[] */
+	uint32_t pair_end;              /* one past this BVH's last pair node */
 	uint32_t node_count;            /* reference nodeCount (0, 1 or >1 select the code path, bvh.c:362-387) */
 	uint32_t slot_offset;           /* into tris[] / slot_poly[] (mesh) or top_prims[] (top level) */
 	uint32_t root_first, root_count;/* when node_count == 1: the root is a leaf */
 	float    root_bounds[6];
+	uint32_t stage_base;            /* the first stage_count pair nodes (BFS order = top of the tree) of this BVH are also */
+	uint32_t stage_count;           /* in the staging image at [stage_base, stage_base+stage_count) — see DevScene.stage_img */
 	uint32_t pad;
 };
 
@@ -101,5 +105,8 @@ struct DevScene {
 	const DevMaterial*materials;
 	const crs_node   *nodes;
 	const DevTexture *textures;
+	const PairNode   *stage_img;    /* top-of-tree pair nodes of every BVH, contiguous: K2 copies it into shared memory with one
+	                                   TMA bulk copy (cp.async.bulk) per block; stage_pairs = number of nodes in it */
+	uint32_t          stage_pairs;
 	const float      *u8_to_unit;   /* [256]: (float)i / 255.0f, the byte→float division of texture.c:48-60 done once */
 };

@@ -34,8 +34,9 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
  * its 32 traversal state machines in registers and, whenever fewer than CRG_REFILL lanes are busy, pulls new
  * rays for the idle lanes from a global work counter (one ballot + one atomicAdd per refill, indices handed
  * out in lane order so neighbouring lanes still get neighbouring — coherent — rays). */
-#define CRG_REFILL 24
-#define CRG_NODE_BURST 4
+#define CRG_REFILL 16
+#define CRG_NODE_BURST 3
+#define CRG_STAGE_MIN_RAYS 65536u
 #define CRG_MAX_STEPS 8000000u   /* > 30x the node count of any scene that fits the 2^23-node address space we support */
 
 template <bool COUNT, int MINB>
@@ -48,9 +49,36 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 	__shared__ unsigned s_hist[256];
 	s_hist[threadIdx.x] = 0u;            /* blockDim.x == 256 */
 	__syncthreads();
+	/* ---- stage the top-of-tree pair nodes into shared memory: one TMA bulk copy (cp.async.bulk, SASS UBLKCP) per
+	 *      block, completion signalled on an mbarrier; skipped for the small tail launches where it cannot pay off */
+	extern __shared__ __align__(128) unsigned char s_dyn[];
+	__shared__ __align__(8) unsigned long long s_mbar;
+	const PairNode *snodes = nullptr;
+	if (sc.stage_pairs && n >= CRG_STAGE_MIN_RAYS) {
+		const unsigned bytes = sc.stage_pairs * (unsigned)sizeof(PairNode);
+		const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar);
+		const unsigned dst = (unsigned)__cvta_generic_to_shared(s_dyn);
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+						 ::"r"(dst), "l"(sc.stage_img), "r"(bytes), "r"(mbar) : "memory");
+		}
+		unsigned ok = 0u;
+		while (!ok) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+						 : "=r"(ok) : "r"(mbar) : "memory");
+		}
+		snodes = reinterpret_cast<const PairNode *>(s_dyn);
+	}
 	uint32_t stack[2 * CRG_MAX_STACK + 2];
 	Traversal<COUNT> tr;
 	tr.stack = stack;
+	tr.snodes = snodes;
 	tr.begin(sc, v3make(0.f, 0.f, 0.f), v3make(0.f, 0.f, 1.f));   /* every lane holds a VALID (idle) state from the start */
 	bool busy = false;
 	bool exhausted = false;          /* warp-uniform: the work counter ran past n */
@@ -135,17 +163,21 @@ void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDe
 template <bool COUNT, int MINB>
 static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int cur, cudaStream_t st) {
 	static int grid = 0;
-	if (!grid) {
+	static size_t grid_smem = (size_t)-1;
+	const size_t smem = (size_t)sc.stage_pairs * sizeof(PairNode);
+	if (!grid || grid_smem != smem) {
 		int dev = 0, sms = 0, occ = 0;
 		cudaGetDevice(&dev);
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<COUNT, MINB>, 256, 0);
+		cudaFuncSetAttribute(k_trace<COUNT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, CRG_STAGE_PAIRS * (int)sizeof(PairNode));
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<COUNT, MINB>, 256, smem);
 		grid = sms * (occ > 0 ? occ : 1);
+		grid_smem = smem;
 	}
 	static int refill = 0, burst = 0;
 	if (!refill) { const char *e = getenv("CRGPU_TRACE_REFILL"); refill = e ? atoi(e) : CRG_REFILL; if (refill < 1 || refill > 32) refill = CRG_REFILL;
 		e = getenv("CRGPU_TRACE_BURST"); burst = e ? atoi(e) : CRG_NODE_BURST; if (burst < 1) burst = CRG_NODE_BURST; }
-	k_trace<COUNT, MINB><<<grid, 256, 0, st>>>(sc, wb, cur, refill, burst);
+	k_trace<COUNT, MINB><<<grid, 256, smem, st>>>(sc, wb, cur, refill, burst);
 }
 
 void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, int grid, cudaStream_t st) {

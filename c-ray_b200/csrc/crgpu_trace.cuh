@@ -186,6 +186,8 @@ struct Traversal {
 	v3 o, d;               /* ray of the current level */
 	RaySetup rs;
 	const PairNode *__restrict__ base;
+	const PairNode *snodes;        /* shared-memory copy of DevScene.stage_img (NULL: not staged) */
+	uint32_t stageBase, stageCount;/* nodes [0, stageCount) of the current BVH live at snodes[stageBase + node] */
 	const PackedTri *__restrict__ tris;
 	uint32_t slotBase, node, topNext;
 	uint32_t pendA, cntA, pendB, cntB;     /* pending top-level leaf items: A (left leaf) before B (right leaf) */
@@ -200,6 +202,7 @@ struct Traversal {
 		wo = ro; wd = rd; o = ro; d = rd;
 		rs = cr_ray_setup(o, d);
 		base = sc.pairs + sc.top.pair_offset;
+		stageBase = sc.top.stage_base; stageCount = snodes ? sc.top.stage_count : 0u;
 		tris = sc.tris;
 		slotBase = 0u; node = 0u; topNext = CRG_END;
 		pendA = 0u; cntA = 0u; pendB = 0u; cntB = 0u;
@@ -227,9 +230,17 @@ struct Traversal {
 	CRD void node_step(const DevScene &sc, TraceCounters *ctr) {
 		{
 			/* ---- one child-pair step (bvh.c:391-439) */
-			const float4 *p4 = reinterpret_cast<const float4 *>(base + node);
-			const float4 q0 = __ldg(p4 + 0), q1 = __ldg(p4 + 1), q2 = __ldg(p4 + 2);
-			const uint4 q3 = __ldg(reinterpret_cast<const uint4 *>(p4 + 3));
+			float4 q0, q1, q2;
+			uint4 q3;
+			if (node < stageCount) {                     /* top of the tree: staged in shared memory by TMA */
+				const float4 *p4 = reinterpret_cast<const float4 *>(snodes + stageBase + node);
+				q0 = p4[0]; q1 = p4[1]; q2 = p4[2];
+				q3 = *reinterpret_cast<const uint4 *>(p4 + 3);
+			} else {
+				const float4 *p4 = reinterpret_cast<const float4 *>(base + node);
+				q0 = __ldg(p4 + 0); q1 = __ldg(p4 + 1); q2 = __ldg(p4 + 2);
+				q3 = __ldg(reinterpret_cast<const uint4 *>(p4 + 3));
+			}
 			const float lb[6] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y };
 			const float rb[6] = { q1.z, q1.w, q2.x, q2.y, q2.z, q2.w };
 			if (COUNT) ctr->pairs++;
@@ -258,6 +269,7 @@ struct Traversal {
 					o = wo; d = wd;
 					rs = cr_ray_setup(o, d);
 					base = sc.pairs + sc.top.pair_offset;
+					stageBase = sc.top.stage_base; stageCount = snodes ? sc.top.stage_count : 0u;
 					node = topNext;
 					spBase = 0;
 				}
@@ -303,6 +315,7 @@ struct Traversal {
 					o = oo; d = od;
 					rs = cr_ray_setup(o, d);
 					base = sc.pairs + __ldg(&bvh->pair_offset);
+					stageBase = __ldg(&bvh->stage_base); stageCount = snodes ? __ldg(&bvh->stage_count) : 0u;
 					tris = sc.tris + slotOff;
 					slotBase = slotOff;
 					curInst = cur;
@@ -323,6 +336,7 @@ CRD Hit cr_closest_hit(const DevScene &sc, v3 wo, v3 wd, TraceCounters *ctr) {
 	uint32_t stack[2 * CRG_MAX_STACK + 2];
 	Traversal<COUNT> tr;
 	tr.stack = stack;
+	tr.snodes = nullptr;
 	tr.begin(sc, wo, wd);
 	while (!tr.done()) tr.step(sc, ctr);
 	return tr.best;

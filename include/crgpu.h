@@ -87,10 +87,12 @@ int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 int crgpu_render_tiles(crgpu_scene *s, const int *rects, int nrects,
 					   int pass_begin, int pass_count, unsigned flags, struct crgpu_stats *stats);
 
-/* Run on a caller-owned CUDA stream (a `cudaStream_t` passed as void*; NULL restores the scene's own
- * stream).  Lets a host that already has a stream (e.g. the one its NCCL collectives use) order the
- * kernels with its own work and time them with its own events. */
+/* Run on a caller-owned CUDA stream (a `cudaStream_t` passed as void*; NULL means the legacy default
+ * stream, as everywhere in CUDA).  Lets a host that already has a stream (e.g. the one its NCCL collectives
+ * use) order the kernels with its own work and time them with its own events.  crgpu_use_own_stream goes
+ * back to the scene's private non-blocking stream. */
 int crgpu_set_stream(crgpu_scene *s, void *cuda_stream);
+int crgpu_use_own_stream(crgpu_scene *s);
 /* Synchronise the stream and return the statistics accumulated since the previous fetch (by
  * crgpu_get_stats or by a synchronous crgpu_render_tile). */
 int crgpu_get_stats(crgpu_scene *s, struct crgpu_stats *stats);

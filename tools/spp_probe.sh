@@ -1,14 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-run() { # name envs...
-  env "$@" timeout 200 python bench.py --workload ${WL:-hdr} --spp 256 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bq.json 2>gpurun_out/bq.err; python -c "
-import json;d=json.load(open('gpurun_out/bq.json'));print('$* ${WL:-hdr}', d['value'], d['ms_per_step'], d['roofline']['trace_gray_per_s'], d['roofline']['trace_share_of_step'])"; tail -1 gpurun_out/bq.err; }
-run CRGPU_TRACE_BURST=1 CRGPU_TRACE_REFILL=16
-run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=16
-run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=8
-run CRGPU_TRACE_BURST=1 CRGPU_TRACE_REFILL=8
-run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=12
-run CRGPU_TRACE_BURST=3 CRGPU_TRACE_REFILL=16
-WL=venus run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=16
-WL=venus run CRGPU_TRACE_BURST=4 CRGPU_TRACE_REFILL=24
-WL=venus run CRGPU_TRACE_BURST=2 CRGPU_TRACE_REFILL=8
+timeout 100 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest.log
+timeout 400 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; cat gpurun_out/bench_n1.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','msample_per_s','gpu_launches','clocks')}); print(d['e2e']); print(d['roofline']); print(d.get('cpu_baseline'))"; tail -3 gpurun_out/bench_n1.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --spp 128 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu rc=$?"
