@@ -10,6 +10,7 @@
 #define CRG_NODE_DEPTH 3
 #define CRG_ADD_STACK 4
 #define CRG_HITKAT_BYTES 160
+#define CRG_TAIL_FROM 6      /* first bounce at which the tail kernel may take over (it only does when <= 16384 rays are left) */
 
 #include <cstdio>
 #include <cstdlib>
@@ -558,6 +559,7 @@ static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, in
 		crg_launch_generate(s->dev, s->wb, td, grid, st); ++launches;
 		int cur = 0;
 		for (int depth = 0; depth < maxDepth; ++depth) {
+			if (depth >= CRG_TAIL_FROM && !count) { crg_launch_tail(s->dev_copy, s->wb, cur, depth, maxDepth, st); ++launches; }
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
 			crg_launch_trace(s->dev, s->wb, cur, count, grid, st);
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }

@@ -43,6 +43,56 @@ __global__ void __launch_bounds__(256) k_bucket(WaveBuffers wb, int cur) {
 	}
 }
 
+/* ---- one bounce of pathTrace's loop body for one path (pathtrace.c:38-57), shared by K3 and the tail kernel -----------------
+ * Radiance goes to L[path id].  The reference accumulates into finalColor = (0,0,0) (pathtrace.c:34); the first
+ * contribution is therefore written as 0.0f + x (bit-identical, also for x = -0) WITHOUT reading L, and the top bit
+ * of the carried id remembers that L holds a value; a path that ends without any contribution writes zeros.  So K1
+ * never has to clear L and most paths touch their L record exactly once. */
+#define CRG_ID_HAS_L 0x80000000u
+
+CRD void cr_add_radiance(float4 *__restrict__ Lbuf, unsigned &id, float r, float g, float b) {
+	const unsigned slot = id & ~CRG_ID_HAS_L;
+	float4 L = (id & CRG_ID_HAS_L) ? Lbuf[slot] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	L.x = L.x + r; L.y = L.y + g; L.z = L.z + b;
+	Lbuf[slot] = L;
+	id |= CRG_ID_HAS_L;
+}
+CRD void cr_finish_path(float4 *__restrict__ Lbuf, unsigned id) {
+	if (!(id & CRG_ID_HAS_L)) Lbuf[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+/* returns true when the path continues with (p_next, d_next) and the updated weight / rng / id */
+CRD bool cr_shade_one(const DevScene &sc, float4 *__restrict__ Lbuf, v3 o, v3 d, const Hit &hit, float &wr, float &wg, float &wbl,
+					  unsigned &id, uint64_t &rng, int depth, int maxDepth, v3 &p_next, v3 &d_next) {
+	if (hit.inst < 0) {                                                               /* pathtrace.c:39-42 */
+		const col4 bg = cr_sample_background(sc, d);
+		cr_add_radiance(Lbuf, id, wr * bg.r, wg * bg.g, wbl * bg.b);
+		return false;
+	}
+	Rec rec;
+	const int material = cr_reconstruct_hit(sc, o, d, hit, rec, false);
+	const DevMaterial mat = sc.materials[material];
+	if (mat.flags & 2u)                                                               /* pathtrace.c:44 (x + w*0 == x) */
+		cr_add_radiance(Lbuf, id, wr * mat.emission[0], wg * mat.emission[1], wbl * mat.emission[2]);
+	if (depth + 1 < maxDepth) {                                                       /* else: the loop ends, the sample is unused */
+		const BsdfSample s = cr_sample_bsdf(sc, mat.bsdf, rng, rec);                 /* pathtrace.c:46-48 */
+		float probability = 1.0f;
+		bool cont = true;
+		if (depth >= 4) {                                                             /* pathtrace.c:50-55 */
+			probability = CR_MAX(s.color.r, CR_MAX(s.color.g, s.color.b));
+			if (cr_draw(rng) > probability) cont = false;
+		}
+		if (cont) {
+			const float inv = cr_div(1.0f, probability);                              /* pathtrace.c:57 */
+			wr = (s.color.r * wr) * inv; wg = (s.color.g * wg) * inv; wbl = (s.color.b * wbl) * inv;
+			p_next = rec.p; d_next = s.out;
+			return true;
+		}
+	}
+	cr_finish_path(Lbuf, id);
+	return false;
+}
+
 /* ---- K3 (+ compaction) ---------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(256) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth) {
 	const DevScene &sc = *scp;
@@ -69,55 +119,63 @@ __global__ void __launch_bounds__(256) k_shade(const DevScene *__restrict__ scp,
 			Hit hit;
 			hit.t = hq.x; hit.u = hq.y; hit.v = hq.z; hit.prim = __float_as_uint(hq.w);
 			hit.inst = wb.hitInst[i];
-			const v3 o = v3make(a.x, a.y, a.z), d = v3make(a.w, b.x, b.y);
 			wr = b.z; wg = b.w; wbl = __uint_as_float(c.x);
 			id = c.y;
 			rng = (uint64_t)c.z | ((uint64_t)c.w << 32);
-			if (hit.inst < 0) {                                                               /* pathtrace.c:39-42 */
-				const col4 bg = cr_sample_background(sc, d);
-				float4 L = wb.L[id];
-				L.x = L.x + wr * bg.r; L.y = L.y + wg * bg.g; L.z = L.z + wbl * bg.b;
-				wb.L[id] = L;
-			} else {
-				Rec rec;
-				const int material = cr_reconstruct_hit(sc, o, d, hit, rec, false);
-				const DevMaterial mat = sc.materials[material];
-				if (mat.flags & 2u) {                                                         /* pathtrace.c:44 (x+0 == x) */
-					float4 L = wb.L[id];
-					L.x = L.x + wr * mat.emission[0]; L.y = L.y + wg * mat.emission[1]; L.z = L.z + wbl * mat.emission[2];
-					wb.L[id] = L;
-				}
-				if (depth + 1 < maxDepth) {                                                   /* else: loop ends, sample unused */
-					const BsdfSample s = cr_sample_bsdf(sc, mat.bsdf, rng, rec);             /* pathtrace.c:46-48 */
-					float probability = 1.0f;
-					bool cont = true;
-					if (depth >= 4) {                                                         /* pathtrace.c:50-55 */
-						probability = CR_MAX(s.color.r, CR_MAX(s.color.g, s.color.b));
-						if (cr_draw(rng) > probability) cont = false;
-					}
-					if (cont) {
-						const float inv = cr_div(1.0f, probability);                          /* pathtrace.c:57 */
-						wr = (s.color.r * wr) * inv; wg = (s.color.g * wg) * inv; wbl = (s.color.b * wbl) * inv;
-						p_next = rec.p; d_next = s.out;
-						alive = true;
-					}
-				}
-			}
+			alive = cr_shade_one(sc, wb.L, v3make(a.x, a.y, a.z), v3make(a.w, b.x, b.y), hit, wr, wg, wbl, id, rng, depth, maxDepth, p_next, d_next);
 		}
-		/* K4: order-preserving warp compaction, one atomic per warp */
+		/* order-preserving warp compaction, one atomic per warp */
 		const unsigned mask = __ballot_sync(0xffffffffu, alive);
 		if (mask) {
 			unsigned base = 0u;
 			if (lane == 0u) base = atomicAdd(&wb.counts[nxt], (unsigned)__popc(mask));
 			base = __shfl_sync(0xffffffffu, base, 0);
 			if (alive) {
-				const unsigned j = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
-				wb.stA[nxt][j] = make_float4(p_next.x, p_next.y, p_next.z, d_next.x);
-				wb.stB[nxt][j] = make_float4(d_next.y, d_next.z, wr, wg);
-				wb.stC[nxt][j] = make_uint4(__float_as_uint(wbl), id, (unsigned)(rng & 0xffffffffull), (unsigned)(rng >> 32));
+				const unsigned k = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+				wb.stA[nxt][k] = make_float4(p_next.x, p_next.y, p_next.z, d_next.x);
+				wb.stB[nxt][k] = make_float4(d_next.y, d_next.z, wr, wg);
+				wb.stC[nxt][k] = make_uint4(__float_as_uint(wbl), id, (unsigned)(rng & 0xffffffffull), (unsigned)(rng >> 32));
 			}
 		}
 	}
+}
+
+/* ---- tail kernel: when only a handful of paths is left, finish them in ONE launch -------------------------------------------
+ * Late bounces hold few rays (hdr.json: <0.1% of the batch after 10 bounces; refraction.json keeps a trickle alive for
+ * hundreds of bounces), but every bounce still costs three launches and lasts as long as its slowest ray (~0.2 ms).
+ * From bounce CRG_TAIL_FROM on, this kernel is launched before K2: if at most CRG_TAIL_MAX rays are left it runs each
+ * remaining path to completion (trace + shade in a per-thread loop — the same device functions, the same draws) and
+ * zeroes the live count, so the K2/K4/K3 launches that follow find nothing to do. */
+#define CRG_TAIL_MAX 16384u
+
+__global__ void __launch_bounds__(128) k_tail(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth0, int maxDepth) {
+	const DevScene &sc = *scp;
+	const unsigned n = wb.counts[cur];
+	if (n == 0u || n > CRG_TAIL_MAX) return;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const float4 a = wb.stA[cur][i];
+		const float4 b = wb.stB[cur][i];
+		const uint4 c = wb.stC[cur][i];
+		v3 o = v3make(a.x, a.y, a.z), d = v3make(a.w, b.x, b.y);
+		float wr = b.z, wg = b.w, wbl = __uint_as_float(c.x);
+		unsigned id = c.y;
+		uint64_t rng = (uint64_t)c.z | ((uint64_t)c.w << 32);
+		unsigned long long rays = 0ull;
+		for (int depth = depth0; depth < maxDepth; ++depth) {
+			const Hit hit = cr_closest_hit<false>(sc, o, d, nullptr);
+			++rays;
+			v3 p_next, d_next;
+			if (!cr_shade_one(sc, wb.L, o, d, hit, wr, wg, wbl, id, rng, depth, maxDepth, p_next, d_next)) break;
+			o = p_next; d = d_next;
+		}
+		atomicAdd(&wb.stats[0], rays);
+	}
+	/* the last block to finish clears the queue (every block has read n by then) */
+	__shared__ unsigned s_last;
+	__syncthreads();
+	if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&wb.counts[3], 1u) == gridDim.x - 1u; }
+	__syncthreads();
+	if (s_last && threadIdx.x == 0) { wb.counts[cur] = 0u; wb.counts[cur ^ 1] = 0u; wb.counts[3] = 0u; }
 }
 
 /* ---- K5 ------------------------------------------------------------------------------------------------------------------ */
@@ -201,6 +259,9 @@ __global__ void k_kat(const DevScene *__restrict__ scp, const int32_t *__restric
 
 void crg_launch_bucket(const WaveBuffers &wb, int cur, int grid, cudaStream_t st) {
 	k_bucket<<<grid, 256, 0, st>>>(wb, cur);
+}
+void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, cudaStream_t st) {
+	k_tail<<<128, 128, 0, st>>>(dsc, wb, cur, depth, maxDepth);
 }
 void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int grid, cudaStream_t st) {
 	k_shade<<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);

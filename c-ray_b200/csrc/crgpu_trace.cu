@@ -22,9 +22,8 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
 		wb.stA[0][id] = make_float4(o.x, o.y, o.z, d.x);
 		wb.stB[0][id] = make_float4(d.y, d.z, 1.0f, 1.0f);
 		wb.stC[0][id] = make_uint4(__float_as_uint(1.0f), id, (unsigned)(rng & 0xffffffffull), (unsigned)(rng >> 32));
-		wb.L[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counts[0] = n; wb.counts[1] = 0u; wb.counts[2] = 0u; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counts[0] = n; wb.counts[1] = 0u; wb.counts[2] = 0u; wb.counts[3] = 0u; }
 	if (blockIdx.x == 0) { wb.hist[threadIdx.x] = 0u; wb.hist[256 + threadIdx.x] = 0u; }   /* blockDim.x == 256 */
 }
 

@@ -36,7 +36,7 @@ struct WaveBuffers {
 	unsigned char *hitKey;  /* shading bucket of the hit: 0 = miss, else min(material+1, 255) */
 	unsigned *perm;         /* K4 output: live indices grouped by bucket */
 	unsigned *hist;         /* [256] bucket sizes (filled by K2), [256..511] K4 cursors */
-	unsigned *counts;       /* [0],[1]: live counts of the ping-pong halves; [2]: K2's work counter (next ray to hand out) */
+	unsigned *counts;       /* [0],[1]: live counts of the ping-pong halves; [2]: K2's work counter (next ray to hand out); [3]: tail-kernel block counter */
 	unsigned long long *stats; /* [0] rays, [1] pairs, [2] tris, [3] spheres, [4] insts */
 };
 
@@ -56,6 +56,7 @@ __device__ __forceinline__ void crg_pixel_xy(const TileDesc &td, unsigned px, in
 void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDesc &td, int grid, cudaStream_t st);
 void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, int grid, cudaStream_t st);
 void crg_launch_bucket(const WaveBuffers &wb, int cur, int grid, cudaStream_t st);
+void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, cudaStream_t st);
 void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int grid, cudaStream_t st);
 void crg_launch_accumulate(float *fb, const float4 *L, const TileDesc &td, int W, int H, int grid, cudaStream_t st);
 void crg_launch_to_srgb8(const float *fb, uint8_t *out, size_t n, int grid, cudaStream_t st);
