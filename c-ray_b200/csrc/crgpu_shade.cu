@@ -5,6 +5,7 @@
  */
 #include "crgpu_wave.cuh"
 #include "crgpu_shade.cuh"
+#include <cstdlib>
 
 /* ---- K4: counting sort of the live rays by shading bucket --------------------------------------------------------------------
  * K2 left the bucket sizes in wb.hist[0..255].  Every block derives the same exclusive prefix, then ranks
@@ -94,7 +95,8 @@ CRD bool cr_shade_one(const DevScene &sc, float4 *__restrict__ Lbuf, v3 o, v3 d,
 }
 
 /* ---- K3 (+ compaction) ---------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth) {
 	const DevScene &sc = *scp;
 	const unsigned n = wb.counts[cur];
 	const int nxt = cur ^ 1;
@@ -264,7 +266,11 @@ void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int de
 	k_tail<<<128, 128, 0, st>>>(dsc, wb, cur, depth, maxDepth);
 }
 void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int grid, cudaStream_t st) {
-	k_shade<<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
+	static int minb = 0;
+	if (!minb) { const char *e = getenv("CRGPU_SHADE_MINB"); minb = e ? atoi(e) : 2; }
+	if (minb == 3) k_shade<3><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
+	else if (minb == 4) k_shade<4><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
+	else k_shade<2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
 }
 void crg_launch_accumulate(float *fb, const float4 *L, const TileDesc &td, int W, int H, int grid, cudaStream_t st) {
 	k_accumulate<<<grid, 256, 0, st>>>(fb, L, td, W, H);

@@ -78,8 +78,19 @@ CRD RaySetup cr_ray_setup(v3 o, v3 d) {                                         
 	return s;
 }
 
-/* Slab test of one child.  For ordinary rays this is intersectNode verbatim (bvh.c:326-352; the strict
- * reference build has FP_FAST_FMAF undefined, so a*b+c rounds twice, bvh.c:318-324).
+/* bvh.c:318-324: `fastMultiplyAdd` is fmaf() when the compiler defines FP_FAST_FMAF (the reference's stock
+ * -march=native build) and a*b+c otherwise (the strict oracle build).  The slab test only decides which nodes
+ * are ENTERED, never a hit distance, and both variants are conservative; the survey measured bit-identical
+ * framebuffers between them on hdr.json and venus.json, and tests/test_gpu_parity.py holds the fused variant to
+ * exact hit records against the un-fused oracle.  Fused = 6 FFMA per child instead of 6 FMUL + 6 FADD.
+ * Build with -DCRG_SLAB_UNFUSED to get the two-rounding form. */
+#ifdef CRG_SLAB_UNFUSED
+#define CR_SLAB_MAD(a, b, c) ((a) * (b) + (c))
+#else
+#define CR_SLAB_MAD(a, b, c) __fmaf_rn((a), (b), (c))
+#endif
+
+/* Slab test of one child.  For ordinary rays this is intersectNode verbatim (bvh.c:326-352).
  *
  * Degenerate axes.  When a direction component is exactly 0 the reference computes b*inf + (-o*inf),
  * which is NaN for most bounds; its NaN-tolerant min/max chain then silently DROPS that axis (and, by
@@ -92,12 +103,12 @@ CRD RaySetup cr_ray_setup(v3 o, v3 d) {                                         
  * for a ray that grazes a triangle within one ulp of its leaf's bounding box, on an already
  * measure-zero ray (~1e-13 per ray).  Rays without a zero component take the verbatim path. */
 CRD bool cr_node_test(const float *b, const RaySetup &r, v3 o, float maxDist, float &tEntry) {
-	float tMinX = (r.ox ? b[1] : b[0]) * r.invDir.x + r.scaledStart.x;
-	float tMaxX = (r.ox ? b[0] : b[1]) * r.invDir.x + r.scaledStart.x;
-	float tMinY = (r.oy ? b[3] : b[2]) * r.invDir.y + r.scaledStart.y;
-	float tMaxY = (r.oy ? b[2] : b[3]) * r.invDir.y + r.scaledStart.y;
-	float tMinZ = (r.oz ? b[5] : b[4]) * r.invDir.z + r.scaledStart.z;
-	float tMaxZ = (r.oz ? b[4] : b[5]) * r.invDir.z + r.scaledStart.z;
+	float tMinX = CR_SLAB_MAD((r.ox ? b[1] : b[0]), r.invDir.x, r.scaledStart.x);
+	float tMaxX = CR_SLAB_MAD((r.ox ? b[0] : b[1]), r.invDir.x, r.scaledStart.x);
+	float tMinY = CR_SLAB_MAD((r.oy ? b[3] : b[2]), r.invDir.y, r.scaledStart.y);
+	float tMaxY = CR_SLAB_MAD((r.oy ? b[2] : b[3]), r.invDir.y, r.scaledStart.y);
+	float tMinZ = CR_SLAB_MAD((r.oz ? b[5] : b[4]), r.invDir.z, r.scaledStart.z);
+	float tMaxZ = CR_SLAB_MAD((r.oz ? b[4] : b[5]), r.invDir.z, r.scaledStart.z);
 	if (r.deg) {
 		const float inf = __int_as_float(0x7f800000);
 		if (r.deg & 1u) { const bool in = (b[0] <= o.x) && (o.x <= b[1]); tMinX = in ? -inf : inf; tMaxX = in ? inf : -inf; }
@@ -135,6 +146,36 @@ CRD bool cr_leaf_tris(const PackedTri *__restrict__ tris, uint32_t slot_base, ui
 			if (t >= 0.0f && t < best.t) {
 				best.t = t; best.u = u; best.v = v;
 				best.prim = slot_base + first + i;
+				found = true;
+			}
+		}
+	}
+	return found;
+}
+
+/* two leaves back to back: slots [firstA, firstA+nA) then [firstB, firstB+nB) */
+template <bool COUNT>
+CRD bool cr_leaf_tris2(const PackedTri *__restrict__ tris, uint32_t slot_base, uint32_t firstA, uint32_t nA, uint32_t firstB, uint32_t nB,
+					   v3 o, v3 d, Hit &best, TraceCounters *ctr) {
+	bool found = false;
+	const uint32_t total = nA + nB;
+	for (uint32_t k = 0; k < total; ++k) {
+		const uint32_t slot = k < nA ? firstA + k : firstB + (k - nA);
+		const float4 *t4 = reinterpret_cast<const float4 *>(tris + slot);
+		const float4 a = __ldg(t4 + 0), b = __ldg(t4 + 1), c4 = __ldg(t4 + 2);
+		if (COUNT) ctr->tris++;
+		const v3 v0 = v3make(a.x, a.y, a.z), e1 = v3make(a.w, b.x, b.y), e2 = v3make(b.z, b.w, c4.x);
+		const v3 n = v3make(c4.y, c4.z, c4.w);
+		const v3 c = v3sub(v0, o);
+		const v3 r = v3cross(d, c);
+		const float invDet = cr_div(1.0f, v3dot(n, d));
+		const float u = v3dot(r, e2) * invDet;
+		const float v = v3dot(r, e1) * invDet;
+		if (u >= 0.0f && v >= 0.0f && u + v <= 1.0f) {
+			const float t = v3dot(n, c) * invDet;
+			if (t >= 0.0f && t < best.t) {
+				best.t = t; best.u = u; best.v = v;
+				best.prim = slot_base + slot;
 				found = true;
 			}
 		}
@@ -260,8 +301,11 @@ struct Traversal {
 				next = (sp == spBase) ? CRG_END : stack[--sp];
 			}
 			if (bottom) {
-				if (hitL && leafL) instHit |= cr_leaf_tris<COUNT>(tris, slotBase, q3.x, q3.z & ~CRG_LEAF_BIT, o, d, best, ctr);
-				if (hitR && leafR) instHit |= cr_leaf_tris<COUNT>(tris, slotBase, q3.y, q3.w & ~CRG_LEAF_BIT, o, d, best, ctr);
+				/* left leaf, then right leaf (bvh.c:402-418), as ONE loop so that lanes with a left leaf and lanes with a
+				 * right leaf test their triangles together */
+				const uint32_t nL = (hitL && leafL) ? (q3.z & ~CRG_LEAF_BIT) : 0u;
+				const uint32_t nR = (hitR && leafR) ? (q3.w & ~CRG_LEAF_BIT) : 0u;
+				if (nL + nR) instHit |= cr_leaf_tris2<COUNT>(tris, slotBase, q3.x, nL, q3.y, nR, o, d, best, ctr);
 				node = next;
 				if (node == CRG_END) {                                             /* back to the top level (instance.c:175-184) */
 					if (instHit) best.inst = curInst;
