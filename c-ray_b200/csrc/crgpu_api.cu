@@ -534,8 +534,31 @@ static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, in
 						 unsigned flags, struct crgpu_stats *stats) {
 	if (pass_begin < 0 || pass_count < 0 || (uint64_t)pass_begin + (uint64_t)pass_count > s->dev.sample_count)
 		return fail(CRGPU_ERR_BAD_ARGUMENT, "passes [%d,%d) outside [0,%u)", pass_begin, pass_begin + pass_count, s->dev.sample_count);
-	if (tile_pixels > s->max_paths) return fail(CRGPU_ERR_BAD_ARGUMENT, "pixel set has %llu pixels > max paths in flight %llu: use smaller tiles or raise the limit",
-												(unsigned long long)tile_pixels, (unsigned long long)s->max_paths);
+	if (tile_pixels > s->max_paths) {
+		/* more pixels than paths in flight: walk the pixel set in pieces (rows of the rectangle / ranges of the list) */
+		const unsigned inner = flags | CRGPU_FLAG_ASYNC;
+		if (base.pixels) {
+			for (uint64_t p0 = 0; p0 < tile_pixels; p0 += s->max_paths) {
+				TileDesc part = base;
+				part.pixels = base.pixels + p0;
+				const uint64_t cnt = tile_pixels - p0 < s->max_paths ? tile_pixels - p0 : s->max_paths;
+				int rc = render_pixels(s, part, cnt, pass_begin, pass_count, inner, nullptr);
+				if (rc) return rc;
+			}
+		} else {
+			const uint64_t rows = s->max_paths / (uint64_t)base.tw;
+			if (rows < 1) return fail(CRGPU_ERR_BAD_ARGUMENT, "tile is %d pixels wide > max paths in flight %llu", base.tw, (unsigned long long)s->max_paths);
+			for (int y = 0; y < base.th; y += (int)rows) {
+				TileDesc part = base;
+				part.y0 = base.y0 + y;
+				part.th = base.th - y < (int)rows ? base.th - y : (int)rows;
+				int rc = render_pixels(s, part, (uint64_t)part.tw * (uint64_t)part.th, pass_begin, pass_count, inner, nullptr);
+				if (rc) return rc;
+			}
+		}
+		if (flags & CRGPU_FLAG_ASYNC) return CRGPU_OK;
+		return crgpu_get_stats(s, stats);
+	}
 	uint64_t batch = s->max_paths / tile_pixels;
 	if (batch > (uint64_t)pass_count) batch = (uint64_t)pass_count;
 	if (batch < 1) batch = 1;

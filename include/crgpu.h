@@ -78,7 +78,8 @@ int crgpu_set_max_paths_in_flight(crgpu_scene *s, uint64_t max_paths);
  * exclusive: `struct renderTile`, tile.h:28-37) into the device framebuffer, continuing the running
  * average stored there.  maxPasses and bounces come from the scene prefs (they seed the sampler,
  * sampler.c:42).  Synchronous (returns when the device is done, `stats` = this call) unless
- * CRGPU_FLAG_ASYNC is given.  `stats` may be NULL. */
+ * CRGPU_FLAG_ASYNC is given.  `stats` may be NULL.  A tile with more pixels than the paths-in-flight budget
+ * is walked in pieces internally. */
 int crgpu_render_tile(crgpu_scene *s, int x0, int y0, int x1, int y1,
 					  int pass_begin, int pass_count, unsigned flags, struct crgpu_stats *stats);
 
