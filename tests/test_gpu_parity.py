@@ -144,7 +144,7 @@ FULL_SIZE = [   # BASELINE.json configs[1..4] geometry at reduced spp (the CPU c
 @pytest.mark.parametrize("name,W,H,spp,b,band", FULL_SIZE)
 def test_full_size_invariants(name, W, H, spp, b, band):
     """Full-size frames: properties that do not need the CPU to render the frame — determinism, invariance to the tile
-    decomposition and to the paths-in-flight budget, ray-count bounds, finite non-negative radiance — plus one band of
+    decomposition and to the paths-in-flight budget, ray-count bounds, finite radiance — plus one band of
     rows checked against the oracle on the host cores (same seeds: they depend only on pixel, pass, spp, width)."""
     scene = os.path.join(BUILT, name + ".crscene")
     if not os.path.exists(scene):
@@ -163,7 +163,7 @@ def test_full_size_invariants(name, W, H, spp, b, band):
     assert np.array_equal(bits(a), bits(bimg))
     assert st1["rays"] == st2["rays"] and st1["paths"] == W * H * spp
     assert st1["paths"] <= st1["rays"] <= b * st1["paths"]
-    assert np.isfinite(a).all() and a.min() >= 0.0
+    assert np.isfinite(a).all()     # (negative values are legitimate: texture.c:66-79 extrapolates when x*W-0.5 < 0)
     o = O.OracleScene(scene, W, H, spp, b)
     ref = np.zeros((H, W, 3), np.float32)
     o.render(threads=os.cpu_count(), tile=(0, band[0], W, band[1]), rgb=ref)
