@@ -111,10 +111,15 @@ class GpuScene:
 
     def __init__(self, crscene_path, width=0, height=0, samples=0, bounces=0, device=0, max_paths=None):
         L = lib()
-        self.flat = FlatScene()
-        rc = L.crscene_load(C.byref(self.flat), os.fsencode(crscene_path))
-        if rc != 0:
-            raise CrgpuError(f"crscene_load({crscene_path}) failed: {rc}")
+        if str(crscene_path).lower().endswith(".json"):
+            # a c-ray JSON scene: parsed + BVH-built on the host by libcrloader.so (include/crloader.h)
+            import crscene
+            self.flat = crscene.load_json(crscene_path)
+        else:
+            self.flat = FlatScene()
+            rc = L.crscene_load(C.byref(self.flat), os.fsencode(crscene_path))
+            if rc != 0:
+                raise CrgpuError(f"crscene_load({crscene_path}) failed: {rc}")
         L.crscene_set_config(C.byref(self.flat), width, height, samples, bounces)
         self.W, self.H = self.flat.prefs.image_width, self.flat.prefs.image_height
         self.samples, self.bounces = self.flat.prefs.sample_count, self.flat.prefs.bounces

@@ -1,8 +1,9 @@
 /*
- * cr_main.c — command-line driver of the host mirror: cray_b200 <scene.crscene> [options]
+ * cr_main.c — command-line driver of the host mirror: cray_b200 <scene.json | scene.crscene> [options]
  *
  * The counterpart of reference src/main.c:14-42 for this path: load → renderFrame → writeImage.  The scene
- * is a flattened .crscene (c-ray's JSON/OBJ loading and BVH build are out of scope); the CLI
+ * is either a c-ray JSON scene (parsed and BVH-built by the host loader, c-ray_b200/host/loader/) or a
+ * flattened .crscene (include/crscene.h); the CLI
  * overrides mirror the reference's (-d WxH, -s N, -t WxH, -j N: src/utils/args.c:95-142), with -j counting
  * GPUs instead of CPU threads and -b for the bounce limit the reference only takes from the JSON.
  */
@@ -15,7 +16,7 @@ static int parse_dims(const char *s, int *w, int *h) { return s && sscanf(s, "%d
 
 int main(int argc, char **argv) {
 	if (argc < 2) {
-		fprintf(stderr, "usage: %s scene.crscene [-d WxH] [-s samples] [-b bounces] [-t tileWxtileH] [-j gpus] [-o out.png|out.bmp] [--dump-f32 file] [-q]\n", argv[0]);
+		fprintf(stderr, "usage: %s scene.json|scene.crscene [-d WxH] [-s samples] [-b bounces] [-t tileWxtileH] [-j gpus] [-o out.png|out.bmp] [--dump-f32 file] [-q]\n", argv[0]);
 		return 1;
 	}
 	int W = 0, H = 0, spp = 0, bounces = 0, tw = 0, th = 0, gpus = 1, quiet = 0;

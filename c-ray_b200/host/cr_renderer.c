@@ -10,6 +10,8 @@
  */
 #include "cr_host.h"
 #include "../../include/crgpu_nccl.h"
+#include "../../include/crloader.h"
+#include <strings.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,7 +36,14 @@ struct renderer *newRenderer(void) {                              /* renderer.c:
 
 int loadSceneFile(struct renderer *r, const char *path, int width, int height, int samples, int bounces) {
 	/* the part of loadScene (src/datatypes/scene.c:111-213) that follows parsing + BVH build */
-	if (crscene_load(&r->scene, path) != 0) return -1;
+	size_t n = strlen(path);
+	if (n > 5 && !strcasecmp(path + n - 5, ".json")) {
+		/* a c-ray JSON scene: parse + build both BVH levels on the host (libcrloader.so, include/crloader.h) */
+		if (crloader_load_json(&r->scene, path) != 0) {
+			fprintf(stderr, "cray_b200: %s\n", crloader_last_error());
+			return -1;
+		}
+	} else if (crscene_load(&r->scene, path) != 0) return -1;
 	crscene_set_config(&r->scene, width, height, samples, bounces);
 	r->prefs.imageWidth = r->scene.prefs.image_width;
 	r->prefs.imageHeight = r->scene.prefs.image_height;

@@ -1,0 +1,27 @@
+/*
+ * crloader.h — the scene loader's C ABI (c-ray_b200/libcrloader.so, sources in c-ray_b200/host/loader/).
+ *
+ * Builds the flat scene of crscene.h straight from a c-ray JSON scene file and the OBJ/MTL/PNG/HDR assets it names:
+ * the job of the reference's loadScene (reference src/datatypes/scene.c:121-212 -> parseJSON,
+ * src/utils/loaders/sceneloader.c:1153-1203) including both BVH levels (src/accelerators/bvh.c:245-315).
+ * Pure host C (zlib + libm), no CUDA: the result is handed to crgpu_scene_create (crgpu.h) or crscene_save.
+ *
+ * Asset paths resolve like the reference's: meshes and the HDR environment relative to the JSON file
+ * (sceneloader.c:698,905), textures named inside node graphs relative to the working directory (:783,:826).
+ */
+#pragma once
+#include "crscene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 0 on success, negative on error (message in crloader_last_error()).  Release with crscene_free (or free(out->owner)).
+ * CLI-style overrides (-d WxH, -s N) are applied afterwards with crscene_set_config, which is arithmetically the
+ * same as the reference applying them before newCamera (sceneloader.c:425-467, camera.c:22-42). */
+int crloader_load_json(struct crs_scene *out, const char *json_path);
+const char *crloader_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif

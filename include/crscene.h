@@ -189,6 +189,7 @@ void crscene_free(struct crs_scene *s);
 /* -d WxH / -s N / bounces override on a loaded scene (camera.c:22-42 arithmetic); <= 0 keeps the value */
 int  crscene_set_config(struct crs_scene *s, int width, int height, int samples, int bounces);
 
+
 #ifdef __cplusplus
 }
 #endif
