@@ -88,6 +88,10 @@ typedef void (*crl_bbox_fn)(void *user, unsigned i, bbox3 *bbox, vec3 *center);
 int crl_build_bvh(void *user, crl_bbox_fn fn, unsigned count,
                   struct crs_bvh_node **nodes, uint32_t *node_count, int32_t **prims);
 
+/* cr_threads.c */
+int crl_thread_count(void);
+void crl_parallel_for(int n, void (*fn)(void *arg, int index), void *arg);
+
 /* cr_nodes.c */
 int crl_const_color(struct crl_ctx *c, struct crl_color col);
 int crl_image(struct crl_ctx *c, int tex, uint32_t options);                      /* -1 when tex < 0 (image.c:51) */

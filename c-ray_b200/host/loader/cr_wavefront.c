@@ -194,6 +194,10 @@ static int load_mtl(struct crl_ctx *c, const char *path, struct crl_material **o
 }
 
 /* ---- OBJ --------------------------------------------------------------------------------------------- */
+/* The 23 MB Venus mesh of the headline scene is ~1.2 M lines; parsing is split over threads by cutting the text at
+ * line boundaries.  Pass 1 (parallel) counts per chunk what the reference's count()/countPolygons() count and what its
+ * parse loop will emit; a serial step turns that into output offsets and resolves mtllib/usemtl in file order; pass 2
+ * (parallel) parses every chunk into its slice.  The result is independent of the number of chunks. */
 static int fix_index(size_t max, int old) {              /* wavefront.c:104-113 */
 	if (old == 0) return -1;
 	if (old < 0) return (int)max + old;
@@ -205,85 +209,219 @@ static int find_material(const struct crl_material *set, int count, const char *
 	return 0;
 }
 
+/* in-place tokens of one line: `len` bytes at `buf`, delimiters already replaced by NULs */
+struct ltoks { char *buf; size_t len, count, cur; char *pos; };
+static char *lt_first(struct ltoks *t) { t->cur = 0; t->pos = t->buf; return t->buf; }
+static char *lt_peek(struct ltoks *t) { return t->cur + 1 >= t->count ? NULL : t->pos + strlen(t->pos) + 1; }
+static char *lt_next(struct ltoks *t) { char *n = lt_peek(t); if (n) { t->pos = n; t->cur++; } return n; }
+static void lt_split(struct ltoks *t, char *line, size_t len, char delim) {
+	t->buf = line; t->len = len; t->count = 1;
+	for (size_t i = 0; i < len; ++i) if (line[i] == delim) { line[i] = '\0'; t->count++; }
+	line[len] = '\0';
+}
+static int lt_float(struct ltoks *t, float *out) {
+	const char *s = lt_next(t);
+	if (!s) return -1;
+	*out = (float)atof(s);
+	return 0;
+}
+
+static inline size_t line_len(const char *p, const char *end) {
+	const char *nl = memchr(p, '\n', (size_t)(end - p));
+	return nl ? (size_t)(nl - p) : (size_t)(end - p);
+}
+static inline int first_is(const char *p, size_t len, const char *word, size_t wlen) {
+	return len >= wlen && !memcmp(p, word, wlen) && (len == wlen || p[wlen] == ' ');
+}
+
+struct mtl_event { char *line; int is_lib; int index; };
+
+struct obj_chunk {
+	char *begin, *end;
+	size_t starts_v, starts_vt, starts_vn, count_polys;   /* count() / countPolygons() */
+	size_t nv, nt, nn, np;                                /* what the parse loop emits */
+	struct mtl_event *events; int nevents, cap;
+	size_t ov, ot, on, op;                                /* output offsets (prefix sums) */
+	int start_material, rc;
+};
+
+struct obj_job {
+	struct obj_chunk *chunks;
+	float *vertices, *texcoords, *normals;
+	struct crs_poly *polys;
+	size_t fileVertices, fileTexCoords, fileNormals, filePolys;
+	int vbase, tbase, nbase;
+};
+
+static void obj_pass1(void *arg, int k) {
+	struct obj_chunk *c = &((struct obj_job *)arg)->chunks[k];
+	for (char *p = c->begin; p < c->end;) {
+		size_t full = line_len(p, c->end), len = full > LINE_MAX_BYTES - 1 ? LINE_MAX_BYTES - 1 : full;
+		if (len && p[0] == 'v') {
+			c->starts_v++;
+			if (len >= 2 && p[1] == 't') c->starts_vt++;
+			if (len >= 2 && p[1] == 'n') c->starts_vn++;
+			if (first_is(p, len, "v", 1)) c->nv++;
+			else if (first_is(p, len, "vt", 2)) c->nt++;
+			else if (first_is(p, len, "vn", 2)) c->nn++;
+		} else if (len && p[0] == 'f') {
+			size_t tokens = 1;
+			for (size_t i = 0; i < len; ++i) tokens += p[i] == ' ';
+			c->count_polys += tokens > 4 ? 2 : 1;
+			if (first_is(p, len, "f", 1)) c->np += tokens - 3;      /* validated in pass 2 */
+		} else if (first_is(p, len, "usemtl", 6) || first_is(p, len, "mtllib", 6)) {
+			if (c->nevents == c->cap) { c->cap = c->cap ? c->cap * 2 : 8; c->events = realloc(c->events, sizeof(*c->events) * (size_t)c->cap); }
+			c->events[c->nevents++] = (struct mtl_event){ p, p[0] == 'm', 0 };
+		}
+		p += full + 1;
+	}
+}
+
+static void obj_pass2(void *arg, int k) {
+	struct obj_job *J = arg;
+	struct obj_chunk *c = &J->chunks[k];
+	size_t nv = c->ov, nt = c->ot, nn = c->on, np = c->op;
+	int material = c->start_material, event = 0;
+	struct ltoks line, spec;
+	for (char *p = c->begin; p < c->end && !c->rc;) {
+		size_t full = line_len(p, c->end), len = full > LINE_MAX_BYTES - 1 ? LINE_MAX_BYTES - 1 : full;
+		char *next = p + full + 1;
+		const char c0 = len ? p[0] : '\0';
+		if (c0 == 'v' || c0 == 'f') {
+			lt_split(&line, p, len, ' ');
+			char *first = lt_first(&line);
+			if (!strcmp(first, "v") || !strcmp(first, "vn")) {
+				float *dst = first[1] ? &J->normals[3 * nn] : &J->vertices[3 * nv];
+				if (lt_float(&line, &dst[0]) || lt_float(&line, &dst[1]) || lt_float(&line, &dst[2])) { c->rc = -1; break; }
+				if (first[1]) nn++; else nv++;
+			} else if (!strcmp(first, "vt")) {
+				float *dst = &J->texcoords[2 * nt];
+				if (lt_float(&line, &dst[0]) || lt_float(&line, &dst[1])) { c->rc = -1; break; }
+				nt++;
+			} else if (!strcmp(first, "f")) {
+				const size_t tris = line.count - 3;            /* wavefront.c:80 */
+				if (line.count < 4 || tris > 2 || np + tris > J->filePolys) { c->rc = -2; break; }
+				int corner[4][3];
+				char *corners[4];
+				for (size_t k2 = 0; k2 < line.count - 1; ++k2) corners[k2] = lt_next(&line);
+				for (size_t k2 = 0; k2 < line.count - 1; ++k2) {   /* each "v/vt/vn" corner, parsed once */
+					char *sp = corners[k2];
+					lt_split(&spec, sp, strlen(sp), '/');
+					const char *sv = lt_first(&spec), *st = lt_next(&spec), *sn = lt_next(&spec);
+					if (!st || !sn) { c->rc = -2; break; }
+					corner[k2][0] = J->vbase + fix_index(J->fileVertices, atoi(sv));
+					corner[k2][1] = J->tbase + fix_index(J->fileTexCoords, atoi(st));
+					corner[k2][2] = J->nbase + fix_index(J->fileNormals, atoi(sn));
+				}
+				if (c->rc) break;
+				static const int pick[2][3] = { { 0, 1, 2 }, { 0, 2, 3 } };   /* quads: (a,b,c),(a,c,d) wavefront.c:84-99 */
+				for (size_t i = 0; i < tris; ++i) {
+					struct crs_poly *poly = &J->polys[np++];
+					for (int j = 0; j < 3; ++j) {
+						poly->v[j] = corner[pick[i][j]][0];
+						poly->t[j] = corner[pick[i][j]][1];
+						poly->n[j] = corner[pick[i][j]][2];
+					}
+					poly->material = (uint32_t)material;
+					poly->has_normals = poly->n[0] != -1;
+				}
+			}
+		} else if (c0 == 'u' || c0 == 'm') {
+			if (event < c->nevents && c->events[event].line == p) {
+				if (!c->events[event].is_lib) material = c->events[event].index;
+				event++;
+			}
+		}
+		p = next;
+	}
+}
+
 int crl_load_obj(struct crl_ctx *c, const char *path, struct crl_mesh *out) {
 	memset(out, 0, sizeof(*out));
 	char *text = read_file(path, NULL);
 	if (!text) return 1;
-	struct lines file;
-	lines_init(&file, text);
 	char *dir = dir_of(path);
-	struct toks *line = malloc(sizeof(*line)), *batch = malloc(sizeof(*batch));
-
-	size_t fileVertices = 0, fileTexCoords = 0, fileNormals = 0, filePolys = 0;
-	for (char *h = lines_first(&file); h; h = lines_next(&file)) {
-		if (starts_with("v", h)) fileVertices++;
-		if (starts_with("vt", h)) fileTexCoords++;
-		if (starts_with("vn", h)) fileNormals++;
-		if (h[0] == 'f') { toks_fill(line, h, ' '); filePolys += line->count > 4 ? 2 : 1; }
+	/* the lines the reference iterates: everything up to the last '\n' (or the whole text if there is none) */
+	size_t len = strlen(text);
+	char *end = text + len;
+	{
+		char *last = NULL;
+		for (char *q = end; q > text; --q) if (q[-1] == '\n') { last = q; break; }
+		if (last) end = last - 1;                             /* exclusive end of the last counted line */
+		else end = text + len;
 	}
-	float *vertices = calloc(fileVertices * 3 + 1, sizeof(float));
-	float *texcoords = calloc(fileTexCoords * 2 + 1, sizeof(float));
-	float *normals = calloc(fileNormals * 3 + 1, sizeof(float));
-	struct crs_poly *polys = calloc(filePolys + 1, sizeof(*polys));
-	size_t nv = 0, nt = 0, nn = 0, np = 0;
-	struct crl_material *materials = NULL;
-	int material_count = 0, current_material = 0, rc = 0;
-	const int vbase = c->vertex_count, tbase = c->texcoord_count, nbase = c->normal_count;
-
-	for (char *head = lines_first(&file); head && !rc; head = lines_next(&file)) {
-		toks_fill(line, head, ' ');
-		char *first = toks_first(line);
-		if (first[0] == '#' || first[0] == '\0' || first[0] == 'o' || first[0] == 'g') continue;
-		if (!strcmp(first, "v") || !strcmp(first, "vn")) {
-			float *dst = first[1] ? &normals[3 * nn] : &vertices[3 * nv];
-			if ((first[1] ? nn >= fileNormals : nv >= fileVertices) ||
-			    next_float(line, &dst[0]) || next_float(line, &dst[1]) || next_float(line, &dst[2])) { rc = -1; break; }
-			if (first[1]) nn++; else nv++;
-		} else if (!strcmp(first, "vt")) {
-			float *dst = &texcoords[2 * nt];
-			if (nt >= fileTexCoords || next_float(line, &dst[0]) || next_float(line, &dst[1])) { rc = -1; break; }
-			nt++;
-		} else if (!strcmp(first, "f")) {
-			size_t tris = line->count - 3;               /* wavefront.c:80 */
-			if (line->count < 4 || tris > 2 || np + tris > filePolys) { rc = -2; break; }
-			for (size_t i = 0; i < tris && !rc; ++i) {
-				struct crs_poly *p = &polys[np++];
-				/* token numbers of the three corners: 1,2,3 then 1,3,4 */
-				const size_t corner[2][3] = { { 1, 2, 3 }, { 1, 3, 4 } };
-				for (int j = 0; j < 3; ++j) {
-					toks_first(line);
-					char *spec = NULL;
-					for (size_t k = 0; k < corner[i][j]; ++k) spec = toks_next(line);
-					if (!spec) { rc = -2; break; }
-					toks_fill(batch, spec, '/');
-					const char *sv = toks_first(batch), *st = toks_next(batch), *sn = toks_next(batch);
-					if (!st || !sn) { rc = -2; break; }
-					p->v[j] = vbase + fix_index(fileVertices, atoi(sv));
-					p->t[j] = tbase + fix_index(fileTexCoords, atoi(st));
-					p->n[j] = nbase + fix_index(fileNormals, atoi(sn));
-				}
-				p->material = (uint32_t)current_material;
-				p->has_normals = p->n[0] != -1;
+	const int threads = crl_thread_count();
+	int nchunks = (len > (1u << 20) && threads > 1) ? threads * 2 : 1;
+	struct obj_job J;
+	memset(&J, 0, sizeof(J));
+	J.chunks = calloc((size_t)nchunks, sizeof(*J.chunks));
+	{
+		char *p = text;
+		for (int k = 0; k < nchunks; ++k) {
+			char *stop = k == nchunks - 1 ? end : text + (size_t)(end - text) * (size_t)(k + 1) / (size_t)nchunks;
+			if (stop < p) stop = p;
+			if (k != nchunks - 1) {                              /* move to the next line start */
+				char *nl = stop < end ? memchr(stop, '\n', (size_t)(end - stop)) : NULL;
+				stop = nl ? nl + 1 : end;
 			}
-		} else if (!strcmp(first, "usemtl")) {
-			current_material = find_material(materials, material_count, toks_peek(line));
-		} else if (!strcmp(first, "mtllib")) {
-			const char *name = toks_peek(line);
-			if (!name) { rc = -1; break; }
-			char *p = concat(dir, name);
-			struct crl_material *set = NULL;
-			int n = 0, mrc = load_mtl(c, p, &set, &n);
-			free(p);
-			if (mrc < 0) { rc = -3; break; }
-			if (mrc == 0) { materials = set; material_count = n; }
-			else { materials = NULL; material_count = 0; }
+			J.chunks[k].begin = p;
+			J.chunks[k].end = stop;
+			p = stop;
 		}
 	}
-	free(line); free(batch); free(dir); free(text);
+	crl_parallel_for(nchunks, obj_pass1, &J);
+
+	struct crl_material *materials = NULL;
+	int material_count = 0, current_material = 0, rc = 0;
+	size_t nv = 0, nt = 0, nn = 0, np = 0;
+	for (int k = 0; k < nchunks && !rc; ++k) {
+		struct obj_chunk *ch = &J.chunks[k];
+		J.fileVertices += ch->starts_v; J.fileTexCoords += ch->starts_vt; J.fileNormals += ch->starts_vn; J.filePolys += ch->count_polys;
+		ch->ov = nv; ch->ot = nt; ch->on = nn; ch->op = np;
+		nv += ch->nv; nt += ch->nt; nn += ch->nn; np += ch->np;
+		ch->start_material = current_material;
+		for (int e = 0; e < ch->nevents && !rc; ++e) {
+			struct mtl_event *ev = &ch->events[e];
+			size_t l = line_len(ev->line, ch->end);
+			if (l > LINE_MAX_BYTES - 1) l = LINE_MAX_BYTES - 1;
+			char *copy = malloc(l + 1);
+			memcpy(copy, ev->line, l); copy[l] = '\0';
+			char *arg = strchr(copy, ' ');                      /* second token: up to the next space */
+			if (arg) { arg++; char *sp = strchr(arg, ' '); if (sp) *sp = '\0'; }
+			if (ev->is_lib) {
+				if (!arg) rc = -1;
+				else {
+					char *p = concat(dir, arg);
+					struct crl_material *set = NULL;
+					int n = 0, mrc = load_mtl(c, p, &set, &n);
+					free(p);
+					if (mrc < 0) rc = -3;
+					else if (mrc == 0) { materials = set; material_count = n; }
+					else { materials = NULL; material_count = 0; }
+				}
+			} else {
+				current_material = find_material(materials, material_count, arg);
+				ev->index = current_material;
+			}
+			free(copy);
+		}
+	}
+	if (!rc && (nv > J.fileVertices || nt > J.fileTexCoords || nn > J.fileNormals || np > J.filePolys)) rc = -2;
+	if (!rc) {
+		J.vertices = calloc(J.fileVertices * 3 + 1, sizeof(float));
+		J.texcoords = calloc(J.fileTexCoords * 2 + 1, sizeof(float));
+		J.normals = calloc(J.fileNormals * 3 + 1, sizeof(float));
+		J.polys = calloc(J.filePolys + 1, sizeof(*J.polys));
+		J.vbase = c->vertex_count; J.tbase = c->texcoord_count; J.nbase = c->normal_count;
+		crl_parallel_for(nchunks, obj_pass2, &J);
+		for (int k = 0; k < nchunks; ++k) if (J.chunks[k].rc && !rc) rc = J.chunks[k].rc;
+	}
+	for (int k = 0; k < nchunks; ++k) free(J.chunks[k].events);
+	free(J.chunks); free(dir); free(text);
 	if (rc) {
 		if (rc == -2) snprintf(c->err, sizeof(c->err), "%s: faces must be triangles or quads written v/vt/vn or v//vn", path);
 		else if (rc == -1) snprintf(c->err, sizeof(c->err), "%s: malformed OBJ statement", path);
-		free(vertices); free(texcoords); free(normals); free(polys);
+		free(J.vertices); free(J.texcoords); free(J.normals); free(J.polys);
 		return -1;
 	}
 
@@ -294,21 +432,21 @@ int crl_load_obj(struct crl_ctx *c, const char *path, struct crl_mesh *out) {
 		materials[0].texture = materials[0].specular_map = materials[0].bsdf = -1;
 		material_count = 1;
 	}
-	out->polys = polys;
-	out->poly_count = (int)filePolys;
+	out->polys = J.polys;
+	out->poly_count = (int)J.filePolys;
 	out->materials = materials;
 	out->material_count = material_count;
 	out->texcoord_count = (int)nt;
 
-	c->vertices = realloc(c->vertices, ((size_t)c->vertex_count + fileVertices + 1) * 3 * sizeof(float));
-	memcpy(c->vertices + 3 * (size_t)c->vertex_count, vertices, fileVertices * 3 * sizeof(float));
-	c->normals = realloc(c->normals, ((size_t)c->normal_count + fileNormals + 1) * 3 * sizeof(float));
-	memcpy(c->normals + 3 * (size_t)c->normal_count, normals, fileNormals * 3 * sizeof(float));
-	c->texcoords = realloc(c->texcoords, ((size_t)c->texcoord_count + fileTexCoords + 1) * 2 * sizeof(float));
-	memcpy(c->texcoords + 2 * (size_t)c->texcoord_count, texcoords, fileTexCoords * 2 * sizeof(float));
-	c->vertex_count += (int)fileVertices;
-	c->normal_count += (int)fileNormals;
-	c->texcoord_count += (int)fileTexCoords;
-	free(vertices); free(normals); free(texcoords);
+	c->vertices = realloc(c->vertices, ((size_t)c->vertex_count + J.fileVertices + 1) * 3 * sizeof(float));
+	memcpy(c->vertices + 3 * (size_t)c->vertex_count, J.vertices, J.fileVertices * 3 * sizeof(float));
+	c->normals = realloc(c->normals, ((size_t)c->normal_count + J.fileNormals + 1) * 3 * sizeof(float));
+	memcpy(c->normals + 3 * (size_t)c->normal_count, J.normals, J.fileNormals * 3 * sizeof(float));
+	c->texcoords = realloc(c->texcoords, ((size_t)c->texcoord_count + J.fileTexCoords + 1) * 2 * sizeof(float));
+	memcpy(c->texcoords + 2 * (size_t)c->texcoord_count, J.texcoords, J.fileTexCoords * 2 * sizeof(float));
+	c->vertex_count += (int)J.fileVertices;
+	c->normal_count += (int)J.fileNormals;
+	c->texcoord_count += (int)J.fileTexCoords;
+	free(J.vertices); free(J.normals); free(J.texcoords);
 	return 0;
 }

@@ -484,6 +484,55 @@ def test_fuzz_against_live_reference(seed, tmp_path, monkeypatch):
     crscene.free(mine)
 
 
+def _big_scene(d, rng, tris=60000):
+    """One mesh big enough (> 1 MB of text, > 8192 triangles) to take the loader's multi-threaded parse and BVH build."""
+    lines = ["mtllib big.mtl", "o big"]
+    nv = tris // 2 + 3
+    for i in range(nv):
+        a = i * 0.001
+        lines.append("v %.6f %.6f %.6f" % (math.cos(a * 7) * (1 + a), rng.uniform(-1, 1), math.sin(a * 5) * (1 + 0.5 * a)))
+    lines += ["vt %.5f %.5f" % (rng.random(), rng.random()) for _ in range(64)]
+    lines += ["vn 0 1 0", "vn 0.6 0.8 0"]
+    for i in range(tris):
+        if i % 5000 == 0: lines.append("usemtl m%d" % ((i // 5000) % 3))
+        a = rng.randrange(nv - 2)
+        if i % 7 == 0:
+            lines.append("f %d/%d/1 %d/%d/2 %d/%d/1 %d/%d/2" % (a + 1, i % 64 + 1, a + 2, (i + 1) % 64 + 1, a + 3, (i + 2) % 64 + 1, (a + 40) % nv + 1, 1))
+        else:
+            lines.append("f %d//1 %d//2 %d//1" % (a + 1, a + 2, (a + 17) % nv + 1))
+    open(os.path.join(d, "big.obj"), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(d, "big.mtl"), "w").write("newmtl m0\nKd 0.8 0.1 0.1\nnewmtl m1\nKd 0.1 0.8 0.1\nillum 5\nnewmtl m2\nKd 0.1 0.1 0.8\nillum 7\nNi 1.4\n")
+    scene = {"renderer": {"width": 64, "height": 48, "samples": 2, "bounces": 3}, "camera": {"FOV": 60},
+             "scene": {"ambientColor": {"down": [1, 1, 1], "up": [0.2, 0.3, 1]},
+                       "meshes": [{"fileName": "big.obj", "bsdf": "plastic",
+                                   "instances": [{"transforms": [{"type": "translate", "Z": 6}]},
+                                                 {"transforms": [{"type": "rotateY", "degrees": 30}, {"type": "translate", "X": 4, "Z": 9}]}]}]}}
+    open(os.path.join(d, "big.json"), "w").write(json.dumps(scene))
+
+
+def test_large_mesh_same_for_any_thread_count(tmp_path, monkeypatch):
+    d = str(tmp_path)
+    _big_scene(d, random.Random(5))
+    assert os.path.getsize(os.path.join(d, "big.obj")) > (1 << 20)
+    monkeypatch.chdir(d)
+    scenes = []
+    for threads in ("1", "2", "7"):
+        monkeypatch.setenv("CRLOADER_THREADS", threads)
+        scenes.append(crscene.load_json("big.json"))
+    assert scenes[0].poly_count > 60000 and scenes[0].bvh_node_count > 10000
+    for other in scenes[1:]:
+        A, B = crscene.arrays(scenes[0]), crscene.arrays(other)
+        for key in A:
+            assert A[key].tobytes() == B[key].tobytes(), key
+    if os.path.exists(REF):                                  # and the same as the reference's serial build
+        r = subprocess.run([REF, "export", "big.json", "0", "0", "0", "0", "ref.crscene"], cwd=d, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:]
+        assert_same_scene(scenes[2], load_crscene(os.path.join(d, "ref.crscene")))
+    for s_ in scenes:
+        crscene.free(s_)
+
+
 # ------------------------------------------------------------------------------------------------ GPU end to end
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["g_nodes", "g_meshmat", "g_single"])
