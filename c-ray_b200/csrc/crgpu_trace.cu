@@ -3,6 +3,7 @@
  * Everything here is force-inlined; the scene descriptor travels as a by-value kernel parameter so
  * its pointers sit in the constant bank.
  */
+#include <mutex>
 #include "crgpu_wave.cuh"
 #include "crgpu_trace.cuh"
 #include <cstdlib>
@@ -159,19 +160,30 @@ void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDe
 /* K2 is persistent: the grid is exactly the number of blocks the device can keep resident.  MINB (blocks per SM
  * the compiler must make room for: 2 -> <=128 registers, 3 -> <=80, 4 -> <=64) trades registers for latency-hiding warps;
  * CRGPU_TRACE_MINB=2|3 overrides the default for experiments. */
+#define CRG_MAX_DEVICES 64
 template <bool COUNT, int MINB>
 static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int cur, cudaStream_t st) {
-	static int grid = 0;
-	static size_t grid_smem = (size_t)-1;
+	/* launch shape per DEVICE: the host mirror drives several GPUs from one process (one thread each), and both the
+	 * occupancy answer and the opt-in shared-memory attribute belong to a device, not to the process */
+	struct Shape { int grid; size_t smem; };
+	static Shape shapes[CRG_MAX_DEVICES];
+	static std::mutex shapes_lock;
 	const size_t smem = (size_t)sc.stage_pairs * sizeof(PairNode);
-	if (!grid || grid_smem != smem) {
-		int dev = 0, sms = 0, occ = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		cudaFuncSetAttribute(k_trace<COUNT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, CRG_STAGE_PAIRS * (int)sizeof(PairNode));
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<COUNT, MINB>, 256, smem);
-		grid = sms * (occ > 0 ? occ : 1);
-		grid_smem = smem;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	int grid;
+	{
+		std::lock_guard<std::mutex> guard(shapes_lock);
+		Shape &sh = shapes[dev >= 0 && dev < CRG_MAX_DEVICES ? dev : 0];
+		if (!sh.grid || sh.smem != smem) {
+			int sms = 0, occ = 0;
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			cudaFuncSetAttribute(k_trace<COUNT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, CRG_STAGE_PAIRS * (int)sizeof(PairNode));
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<COUNT, MINB>, 256, smem);
+			sh.grid = sms * (occ > 0 ? occ : 1);
+			sh.smem = smem;
+		}
+		grid = sh.grid;
 	}
 	static int refill = 0, burst = 0;
 	if (!refill) { const char *e = getenv("CRGPU_TRACE_REFILL"); refill = e ? atoi(e) : CRG_REFILL; if (refill < 1 || refill > 32) refill = CRG_REFILL;

@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <pthread.h>
 #include "../../include/crgpu.h"
+#include "../../include/crloader.h"
 
 struct intCoord { int x, y; };
 
@@ -100,7 +101,11 @@ struct renderTile nextTile(struct renderer *r);
 
 /* renderer */
 struct renderer *newRenderer(void);
-int loadSceneFile(struct renderer *r, const char *crscene_path, int width, int height, int samples, int bounces);
+int loadSceneFile(struct renderer *r, const char *json_or_crscene_path, int width, int height, int samples, int bounces);
+int loadSceneBuf(struct renderer *r, const char *json, const char *assetPath, struct crloader_output *output,
+				 int width, int height, int samples, int bounces);   /* loadScene(r, buf), scene.c:121 */
+/* (re)derive prefs, tile grid and host framebuffer from r->scene after -d/-s style overrides (<= 0 keeps a value) */
+int applySceneConfig(struct renderer *r, int width, int height, int samples, int bounces);
 struct texture8 *renderFrame(struct renderer *r);          /* NULL on error */
 void destroyTexture8(struct texture8 *t);
 void destroyRenderer(struct renderer *r);

@@ -34,8 +34,8 @@ struct renderer *newRenderer(void) {                              /* renderer.c:
 	return r;
 }
 
+
 int loadSceneFile(struct renderer *r, const char *path, int width, int height, int samples, int bounces) {
-	/* the part of loadScene (src/datatypes/scene.c:111-213) that follows parsing + BVH build */
 	size_t n = strlen(path);
 	if (n > 5 && !strcasecmp(path + n - 5, ".json")) {
 		/* a c-ray JSON scene: parse + build both BVH levels on the host (libcrloader.so, include/crloader.h) */
@@ -44,6 +44,20 @@ int loadSceneFile(struct renderer *r, const char *path, int width, int height, i
 			return -1;
 		}
 	} else if (crscene_load(&r->scene, path) != 0) return -1;
+	return applySceneConfig(r, width, height, samples, bounces);
+}
+
+int loadSceneBuf(struct renderer *r, const char *json, const char *assetPath, struct crloader_output *output,
+				 int width, int height, int samples, int bounces) {
+	if (crloader_load_json_buf(&r->scene, json, assetPath, output) != 0) {
+		fprintf(stderr, "cray_b200: %s\n", crloader_last_error());
+		return -1;
+	}
+	return applySceneConfig(r, width, height, samples, bounces);
+}
+
+int applySceneConfig(struct renderer *r, int width, int height, int samples, int bounces) {
+	/* the part of loadScene (src/datatypes/scene.c:111-213) that follows parsing + BVH build */
 	crscene_set_config(&r->scene, width, height, samples, bounces);
 	r->prefs.imageWidth = r->scene.prefs.image_width;
 	r->prefs.imageHeight = r->scene.prefs.image_height;

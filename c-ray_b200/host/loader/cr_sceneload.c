@@ -581,23 +581,48 @@ static void ctx_free(struct crl_ctx *c) {
 	free(c->vertices); free(c->normals); free(c->texcoords); free(c->asset_path);
 }
 
+static int load_text(struct crs_scene *out, const char *text, const char *asset_path, const char *what, struct crloader_output *output);
+
 int crloader_load_json(struct crs_scene *out, const char *json_path) {
 	g_err[0] = '\0';
 	if (!out || !json_path) { snprintf(g_err, sizeof(g_err), "null argument"); return -1; }
 	char *text = slurp(json_path);
 	if (!text) { snprintf(g_err, sizeof(g_err), "cannot read %s", json_path); return -2; }
+	char *copy = strdup(json_path);
+	char *assets = join(dirname(copy), "/");                 /* c-ray.c:254-256 */
+	int rc = load_text(out, text, assets, json_path, NULL);
+	free(assets); free(copy); free(text);
+	return rc;
+}
+
+int crloader_load_json_buf(struct crs_scene *out, const char *json_text, const char *asset_path, struct crloader_output *output) {
+	g_err[0] = '\0';
+	if (!out || !json_text) { snprintf(g_err, sizeof(g_err), "null argument"); return -1; }
+	return load_text(out, json_text, asset_path ? asset_path : "./", "<buffer>", output);
+}
+
+static void parse_output(const struct crj *d, struct crloader_output *o) {   /* sceneloader.c:341-424, defaults :190-208 */
+	snprintf(o->file_path, sizeof(o->file_path), "./");
+	snprintf(o->file_name, sizeof(o->file_name), "rendered");
+	o->count = 0;
+	o->type = 1;
+	if (!d) return;
+	const struct crj *j;
+	if (crj_is_string(j = crj_get(d, "outputFilePath"))) snprintf(o->file_path, sizeof(o->file_path), "%s", j->str);
+	if (crj_is_string(j = crj_get(d, "outputFileName"))) snprintf(o->file_name, sizeof(o->file_name), "%s", j->str);
+	if (crj_is_number(j = crj_get(d, "count"))) o->count = j->inum >= 0 ? j->inum : 0;
+	if (crj_is_string(j = crj_get(d, "fileType"))) o->type = !strcmp(j->str, "bmp") ? 0 : 1;
+}
+
+static int load_text(struct crs_scene *out, const char *text, const char *asset_path, const char *what, struct crloader_output *output) {
 	struct crj *json = crj_parse(text);
-	free(text);
-	if (!json) { snprintf(g_err, sizeof(g_err), "%s: JSON syntax error", json_path); return -3; }
+	if (!json) { snprintf(g_err, sizeof(g_err), "%s: JSON syntax error", what); return -3; }
+	if (output) parse_output(crj_get(json, "renderer"), output);
 
 	struct crl_ctx ctx;
 	memset(&ctx, 0, sizeof(ctx));
 	ctx.background = -1;
-	{
-		char *copy = strdup(json_path);
-		ctx.asset_path = join(dirname(copy), "/");
-		free(copy);
-	}
+	ctx.asset_path = strdup(asset_path);
 	struct crs_prefs prefs;
 	struct crs_camera cam;
 	struct crs_bvh_node *top_nodes = NULL;

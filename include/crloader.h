@@ -20,6 +20,19 @@ extern "C" {
  * CLI-style overrides (-d WxH, -s N) are applied afterwards with crscene_set_config, which is arithmetically the
  * same as the reference applying them before newCamera (sceneloader.c:425-467, camera.c:22-42). */
 int crloader_load_json(struct crs_scene *out, const char *json_path);
+
+/* Where and how the reference would save the frame: "renderer".outputFilePath / outputFileName / count / fileType
+ * (sceneloader.c:341-424); the file is <file_path><file_name>_<count %04d>.<png|bmp> (src/utils/encoders/encoder.c:24). */
+struct crloader_output {
+	char file_path[512];
+	char file_name[256];
+	int  count;
+	int  type;                 /* 0 = bmp, 1 = png (enum fileType) */
+};
+
+/* Same, from JSON text already in memory (crLoadSceneFromBuf, reference src/c-ray.c:139-141); `asset_path` is the
+ * directory prefix (with trailing '/') mesh and HDR names are appended to, NULL = "./"; `output` may be NULL. */
+int crloader_load_json_buf(struct crs_scene *out, const char *json_text, const char *asset_path, struct crloader_output *output);
 const char *crloader_last_error(void);
 
 #ifdef __cplusplus
