@@ -129,6 +129,42 @@ def run_reference(scene, W, H, spp, bounces, threads):
     return float(m.group(2)), W * H * spp, int(m.group(1))
 
 
+def scene_ingest(scene):
+    """SURVEY 8(f2), informational: JSON + OBJ/MTL + PNG/HDR + both BVH levels -> flat scene on the host cores,
+    this repository's loader (libcrloader.so) next to the reference's own loader (oracle/_ref harness `export`)."""
+    try:
+        import crscene
+        js = os.path.join(ROOT, "oracle", "_ref", "input", scene + ".json")
+        if not os.path.exists(js):
+            return None
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            flat = crscene.load_json(js)
+            dt = time.perf_counter() - t0
+            polys, nodes = int(flat.poly_count), int(flat.bvh_node_count)
+            crscene.free(flat)
+            best = dt if best is None else min(best, dt)
+        out = {"loader_s": round(best, 3), "threads": os.cpu_count() or 1, "triangles": polys, "bvh_nodes": nodes,
+               "what": f"crloader_load_json(input/{scene}.json): parse + decode + SAH BVH build, best of 3"}
+        exe = os.path.join(ROOT, "oracle", "_ref", "cray_ref_stock")
+        if os.path.exists(exe):
+            tmp = f"/tmp/cray_ref_ingest_{os.getpid()}.crscene"
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "export", js, "0", "0", "0", "0", tmp], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            dt = time.perf_counter() - t0
+            if r.returncode == 0:
+                out["reference_s"] = round(dt, 3)
+                out["reference_what"] = "unmodified reference loader (process start + loadScene + flatten + write), one run"
+            try:
+                os.remove(tmp)
+            except OSError:
+                pass
+        return out
+    except Exception as e:      # informational only: never fail the bench line
+        return {"error": str(e)[:200]}
+
+
 def reference_arm(args, w, rank):
     """bench.py --impl reference: the reference's own CPU implementation of the path, rank 0 only."""
     if rank != 0:
@@ -372,6 +408,10 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_cpu_baseline:
+            ingest = scene_ingest(w["scene"])
+            if ingest:
+                line["scene_ingest"] = ingest
         print(json.dumps(line))
     if dist:
         dist.barrier()
