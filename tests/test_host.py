@@ -121,3 +121,29 @@ def test_encoders_roundtrip(host, tmp_path):
     row = (W * 3 + 3) & ~3
     px = np.frombuffer(raw[54:], dtype=np.uint8).reshape(H, row)[:, :W * 3].reshape(H, W, 3)
     assert np.array_equal(px[::-1, :, ::-1], img)       # bottom-up, BGR (bmp.c:19-71)
+
+
+def test_png_encoder_multi_band_stream(host, tmp_path):
+    """Images above ~1 MB of scanlines are deflated in parallel bands (one IDAT each); the concatenation must be ONE valid
+    zlib stream (header, byte-aligned blocks, combined Adler-32) that any decoder accepts."""
+    rng = np.random.default_rng(11)
+    H, W = 1100, 700                                            # 2.3 MB of scanlines -> 3 bands
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.clip(((xx * 255 // W)[..., None] + rng.integers(-9, 10, (H, W, 3))), 0, 255).astype(np.uint8)
+    t = Texture8(W, H, img.ctypes.data_as(C.POINTER(C.c_uint8)))
+    p = str(tmp_path / "big.png")
+    assert host.writeImage(C.byref(t), p.encode(), 1) == 0
+    raw = open(p, "rb").read()
+    assert raw.count(b"IDAT") >= 3
+    assert np.array_equal(decode_png(p), img)                    # zlib.decompress checks the Adler-32 trailer
+    # and through this repository's own PNG decoder (the scene loader's)
+    import crscene, json
+    sc = tmp_path / "s.json"
+    sc.write_text(json.dumps({"renderer": {"width": 4, "height": 4}, "camera": {}, "scene": {"primitives": [
+        {"type": "sphere", "radius": 1, "instances": [{}], "material": {"type": "diffuse", "color": {"type": "image", "path": p}}}]}}))
+    s_ = crscene.load_json(str(sc))
+    A = crscene.arrays(s_)
+    tex = A["textures"][0]
+    assert (tex["width"], tex["height"], tex["channels"]) == (W, H, 3)
+    assert np.array_equal(A["texdata"][int(tex["data_offset"]):int(tex["data_offset"]) + H * W * 3].reshape(H, W, 3), img)
+    crscene.free(s_)
