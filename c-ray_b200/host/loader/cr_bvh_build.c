@@ -51,6 +51,51 @@ static inline void make_leaf(struct crs_bvh_node *n, unsigned begin, unsigned co
 
 struct builder { const bbox3 *bboxes; const vec3 *centers; int32_t *prims; };
 
+/* Bin filling (bvh.c:158-171) for prims[begin,end) on the three axes. */
+static void fill_bins(const struct builder *B, const float bounds[6], unsigned begin, unsigned end, struct bin bins[3][BIN_COUNT]) {
+	for (int axis = 0; axis < 3; ++axis) {
+		struct bin *ab = bins[axis];
+		for (int i = 0; i < BIN_COUNT; ++i) { ab[i].bbox = crl_empty_bbox; ab[i].count = 0; }
+		const float lo = bounds[axis * 2], scale = BIN_COUNT / (bounds[axis * 2 + 1] - lo);
+		for (unsigned i = begin; i < end; ++i) {
+			const int p = B->prims[i];
+			struct bin *b = &ab[bin_index(axis_of(&B->centers[p], axis), lo, scale)];
+			bbox_extend(&b->bbox, &B->bboxes[p]);
+			b->count++;
+		}
+	}
+}
+
+/* The same for the few huge ranges at the top of a big tree, which would otherwise be the serial fraction of the parallel
+ * build: the range is cut into chunks binned concurrently, and the partial bins are merged IN CHUNK ORDER with the same
+ * min/max macros.  Those macros return their second argument on ties, so a left-to-right fold and an ordered fold of
+ * per-chunk folds pick the same element (this matters only for the sign of zero, +0 == -0); counts just add. */
+#define PARALLEL_BIN_PRIMS 32768u
+struct bin_job { const struct builder *B; const float *bounds; unsigned begin, end; int chunks; struct bin (*part)[3][BIN_COUNT]; };
+
+static void bin_chunk(void *arg, int k) {
+	struct bin_job *j = arg;
+	const unsigned n = j->end - j->begin;
+	const unsigned b = j->begin + (unsigned)((unsigned long long)n * (unsigned)k / (unsigned)j->chunks);
+	const unsigned e = j->begin + (unsigned)((unsigned long long)n * (unsigned)(k + 1) / (unsigned)j->chunks);
+	fill_bins(j->B, j->bounds, b, e, j->part[k]);
+}
+
+static void fill_bins_parallel(const struct builder *B, const float bounds[6], unsigned begin, unsigned end, struct bin bins[3][BIN_COUNT]) {
+	int chunks = crl_thread_count();
+	if (chunks > 64) chunks = 64;
+	struct bin_job job = { B, bounds, begin, end, chunks, malloc(sizeof(struct bin) * 3 * BIN_COUNT * (size_t)chunks) };
+	if (!job.part) { fill_bins(B, bounds, begin, end, bins); return; }
+	crl_parallel_for(chunks, bin_chunk, &job);
+	for (int axis = 0; axis < 3; ++axis)
+		for (int i = 0; i < BIN_COUNT; ++i) {
+			struct bin *d = &bins[axis][i];
+			d->bbox = crl_empty_bbox; d->count = 0;
+			for (int k = 0; k < chunks; ++k) { bbox_extend(&d->bbox, &job.part[k][axis][i].bbox); d->count += job.part[k][axis][i].count; }
+		}
+	free(job.part);
+}
+
 /* One node of the reference's buildBvhRecursive (bvh.c:137-243): decide leaf / split for prims[begin,end) inside
  * `bounds`; on a split the range is partitioned in place and the children's boxes are returned.  1 = split, 0 = leaf. */
 static int split_node(const struct builder *B, const float bounds[6], unsigned begin, unsigned end, unsigned depth,
@@ -60,16 +105,10 @@ static int split_node(const struct builder *B, const float bounds[6], unsigned b
 	int32_t *prims = B->prims;
 	float minCost[3] = { FLT_MAX, FLT_MAX, FLT_MAX };
 	unsigned minBin[3] = { 1, 1, 1 };
+	if (primCount >= PARALLEL_BIN_PRIMS && crl_thread_count() > 1) fill_bins_parallel(B, bounds, begin, end, bins);
+	else fill_bins(B, bounds, begin, end, bins);
 	for (int axis = 0; axis < 3; ++axis) {
 		struct bin *ab = bins[axis];
-		for (int i = 0; i < BIN_COUNT; ++i) { ab[i].bbox = crl_empty_bbox; ab[i].count = 0; }
-		const float lo = bounds[axis * 2], scale = BIN_COUNT / (bounds[axis * 2 + 1] - lo);
-		for (unsigned i = begin; i < end; ++i) {
-			const int p = prims[i];
-			struct bin *b = &ab[bin_index(axis_of(&B->centers[p], axis), lo, scale)];
-			bbox_extend(&b->bbox, &B->bboxes[p]);
-			b->count++;
-		}
 		bbox3 cur = crl_empty_bbox;
 		unsigned curCount = 0;
 		for (unsigned i = BIN_COUNT; i > 1; --i) {                /* cost of everything to the right of a split */

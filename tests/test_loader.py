@@ -490,7 +490,10 @@ def _big_scene(d, rng, tris=60000):
     nv = tris // 2 + 3
     for i in range(nv):
         a = i * 0.001
-        lines.append("v %.6f %.6f %.6f" % (math.cos(a * 7) * (1 + a), rng.uniform(-1, 1), math.sin(a * 5) * (1 + 0.5 * a)))
+        # a band of vertices with y exactly +0 / -0 (Blender writes "-0.000000"): the builder's min/max keep the LAST of two
+        # equal values, so the sign of a zero bound depends on visiting order — the threaded build must reproduce it
+        y = rng.choice(["0.000000", "-0.000000"]) if 1000 <= i < 9000 else "%.6f" % rng.uniform(-1, 1)
+        lines.append("v %.6f %s %.6f" % (math.cos(a * 7) * (1 + a), y, math.sin(a * 5) * (1 + 0.5 * a)))
     lines += ["vt %.5f %.5f" % (rng.random(), rng.random()) for _ in range(64)]
     lines += ["vn 0 1 0", "vn 0.6 0.8 0"]
     for i in range(tris):
