@@ -99,6 +99,10 @@ def test_tiling_batching_and_pass_splits_do_not_change_pixels(name):
 
 
 BUNDLED = [("hdr", 240, 135, 16, 32), ("scene", 320, 200, 16, 4), ("refraction", 240, 135, 8, 512), ("venus", 100, 160, 16, 25)]
+# the other five bundled scenes (fixtures exist since late round 1, when no GPU time was left to run them once):
+# opt in with CRAY_GPU_EXTRA=1 until they have been seen green on a B200, then fold them into BUNDLED
+if os.environ.get("CRAY_GPU_EXTRA"):
+    BUNDLED += [(n, 96, 60, 8, 0) for n in ("alphanode", "fence", "glowmetal", "statues", "uvsphere")]
 
 
 @pytest.mark.parametrize("name,W,H,spp,b", BUNDLED)

@@ -133,7 +133,7 @@ def test_golden_scene_matches_reference_export(name, monkeypatch):
     crscene.free(mine)
 
 
-@pytest.mark.parametrize("name", ["hdr", "venus", "refraction", "scene"])
+@pytest.mark.parametrize("name", ["hdr", "venus", "refraction", "scene", "alphanode", "fence", "glowmetal", "statues", "uvsphere"])
 def test_bundled_scene_matches_reference_export(name, monkeypatch):
     src = os.path.join(REF_INPUT, "input", name + ".json")
     exported = os.path.join(BUILT, name + ".crscene")

@@ -92,7 +92,9 @@ def test_srgb8_matches_reference_formula():
     assert np.abs(out.astype(int) - np.array(exp)).max() <= 1
 
 
-@pytest.mark.parametrize("name,W,H,spp,b", [("hdr", 96, 54, 4, 32), ("scene", 80, 50, 4, 4), ("refraction", 64, 36, 2, 512), ("venus", 40, 64, 4, 25)])
+@pytest.mark.parametrize("name,W,H,spp,b", [("hdr", 96, 54, 4, 32), ("scene", 80, 50, 4, 4), ("refraction", 64, 36, 2, 512), ("venus", 40, 64, 4, 25),
+                                            ("alphanode", 96, 60, 8, 0), ("fence", 96, 60, 8, 0), ("glowmetal", 96, 60, 8, 0),
+                                            ("statues", 96, 60, 8, 0), ("uvsphere", 96, 60, 8, 0)])
 def test_bundled_scenes_against_reference_framebuffers(name, W, H, spp, b):
     """Bundled input/*.json scenes: framebuffers rendered by the strict reference in the build container
     (scenes/_built/ref_*.f32, written by __graft_entry__.build) vs the oracle: bit-exact."""
