@@ -5,7 +5,9 @@
  * (reference src/utils/args.c:70-262) and the "current image" handed from crStartRenderer to crWriteImage are the same
  * three pieces of process state the reference keeps (c-ray.c:28-30, args.c:26).
  */
+#ifndef _GNU_SOURCE
 #define _GNU_SOURCE
+#endif
 #include "../../include/cray_api.h"
 #include "cr_host.h"
 #include <libgen.h>

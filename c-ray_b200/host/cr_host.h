@@ -110,6 +110,9 @@ struct texture8 *renderFrame(struct renderer *r);          /* NULL on error */
 void destroyTexture8(struct texture8 *t);
 void destroyRenderer(struct renderer *r);
 
+/* loads libcrgpu_nccl.so (multi-GPU tile gather) on first use; 0 when its entry points are available */
+int crhost_load_nccl(void);
+
 /* worker entry point with the signature of renderThread (void *(*)(void *)) */
 void *gpuRenderThread(void *arg);
 

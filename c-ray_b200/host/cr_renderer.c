@@ -10,12 +10,43 @@
  */
 #include "cr_host.h"
 #include "../../include/crgpu_nccl.h"
+#include <dlfcn.h>
 #include "../../include/crloader.h"
 #include <strings.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+
+/* The NCCL tile gather lives in its own library (libcrgpu_nccl.so) and is loaded on first use: a single-GPU render never
+ * touches NCCL, and a host process that already carries another NCCL build (e.g. a Python host with torch) does not get a
+ * second one mapped just by loading libcrhost.so.  Looked up next to this library, then on the default search path. */
+static struct {
+	void *lib;
+	int (*create)(crgpu_scene **, int, crgpu_comm **);
+	int (*gather)(crgpu_comm *, const int *, const int *, int, int);
+	int (*destroy)(crgpu_comm *);
+} g_nccl;
+
+int crhost_load_nccl(void) {
+	if (g_nccl.gather) return 0;
+	char path[4096] = "";
+	Dl_info info;
+	if (dladdr((void *)crhost_load_nccl, &info) && info.dli_fname) {
+		const char *slash = strrchr(info.dli_fname, '/');
+		if (slash) snprintf(path, sizeof path, "%.*s/libcrgpu_nccl.so", (int)(slash - info.dli_fname), info.dli_fname);
+	}
+	void *lib = path[0] ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : NULL;
+	if (!lib) lib = dlopen("libcrgpu_nccl.so", RTLD_NOW | RTLD_LOCAL);
+	if (!lib) { fprintf(stderr, "renderFrame: cannot load libcrgpu_nccl.so: %s\n", dlerror()); return -1; }
+	g_nccl.create = (int (*)(crgpu_scene **, int, crgpu_comm **))dlsym(lib, "crgpu_comm_create");
+	g_nccl.destroy = (int (*)(crgpu_comm *))dlsym(lib, "crgpu_comm_destroy");
+	void *gather = dlsym(lib, "crgpu_comm_gather_tiles");
+	if (!g_nccl.create || !g_nccl.destroy || !gather) { fprintf(stderr, "renderFrame: libcrgpu_nccl.so lacks the crgpu_comm_* entry points\n"); dlclose(lib); return -1; }
+	g_nccl.lib = lib;
+	g_nccl.gather = (int (*)(crgpu_comm *, const int *, const int *, int, int))gather;
+	return 0;
+}
 
 static double now_s(void) {
 	struct timespec ts;
@@ -190,8 +221,9 @@ struct texture8 *renderFrame(struct renderer *r) {
 				owner[i] = r->state.tileOwner[i];
 			}
 			crgpu_comm *comm = NULL;
-			if (crgpu_comm_create(scenes, n, &comm) != CRGPU_OK || crgpu_comm_gather_tiles(comm, rects, owner, r->state.tileCount, 0) != CRGPU_OK) err = CRGPU_ERR_CUDA;
-			crgpu_comm_destroy(comm);
+			if (crhost_load_nccl() != 0 || g_nccl.create(scenes, n, &comm) != CRGPU_OK ||
+				g_nccl.gather(comm, rects, owner, r->state.tileCount, 0) != CRGPU_OK) err = CRGPU_ERR_CUDA;
+			if (comm) g_nccl.destroy(comm);
 			free(rects); free(owner);
 		}
 		r->state.renderSeconds = now_s() - t0;

@@ -25,6 +25,24 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), f"libcrgpu.so does not export {n}"
 
 
+def test_nccl_library_exports_every_declared_symbol():
+    """include/crgpu_nccl.h -> libcrgpu_nccl.so.  Checked in a subprocess: the library links the system NCCL, and a process
+    that later imports torch (with its own bundled NCCL) must never have both loaded — the reason it is a separate .so."""
+    import subprocess
+    import sys
+    names = declared_symbols("crgpu_nccl.h")
+    assert names == ["crgpu_comm_create", "crgpu_comm_destroy", "crgpu_comm_gather_tiles"]
+    code = ("import ctypes as C, sys\n"
+            "C.CDLL(sys.argv[1] + '/libcrgpu.so', mode=C.RTLD_GLOBAL)\n"
+            "L = C.CDLL(sys.argv[1] + '/libcrgpu_nccl.so')\n"
+            "[getattr(L, n) for n in sys.argv[2:]]\n"
+            "assert L.crgpu_comm_create(None, 0, None) != 0\n"      # bad arguments are rejected before any NCCL call
+            "print('NCCL-ABI-OK')\n")
+    r = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "c-ray_b200")] + names, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert "NCCL-ABI-OK" in r.stdout, r.stdout[-2000:]
+
+
 def test_struct_layouts_match_header():
     assert C.sizeof(crgpu.Stats) == 7 * 8 + 4 * 4
     assert C.sizeof(crgpu.Prefs) == 32 and C.sizeof(crgpu.Camera) == 128

@@ -147,3 +147,20 @@ def test_png_encoder_multi_band_stream(host, tmp_path):
     assert (tex["width"], tex["height"], tex["channels"]) == (W, H, 3)
     assert np.array_equal(A["texdata"][int(tex["data_offset"]):int(tex["data_offset"]) + H * W * 3].reshape(H, W, 3), img)
     crscene.free(s_)
+
+
+def test_nccl_gather_library_is_loaded_on_demand():
+    """libcrhost.so must not map NCCL by itself (a Python host with torch carries its own); the gather library is dlopen'ed
+    by the first multi-GPU frame.  Checked in a subprocess so that this test process never maps the system NCCL."""
+    import subprocess
+    import sys
+    code = ("import ctypes as C, sys\n"
+            "L = C.CDLL(sys.argv[1])\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libnccl' not in maps and 'libcrgpu_nccl' not in maps, 'NCCL mapped by loading libcrhost.so'\n"
+            "assert L.crhost_load_nccl() == 0\n"
+            "assert 'libcrgpu_nccl' in open('/proc/self/maps').read()\n"
+            "print('LAZY-NCCL-OK')\n")
+    r = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "c-ray_b200", "libcrhost.so")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert "LAZY-NCCL-OK" in r.stdout, r.stdout[-2000:]
