@@ -536,6 +536,88 @@ def test_large_mesh_same_for_any_thread_count(tmp_path, monkeypatch):
         crscene.free(s_)
 
 
+# ---- odd but legal inputs: wrong-typed values, missing fields, key case, no-op / unknown transforms, NULL node inputs -------
+def _odd_transforms(rng):
+    out=[]
+    for _ in range(rng.randrange(0,6)):
+        out.append(rng.choice([
+            {"type":"translate"},                       # no coords -> NOP
+            {"type":"translate","x":1.5},              # lower-case keys (case-insensitive lookup)
+            {"type":"rotateX"},                         # no angle -> NOP
+            {"type":"rotateY","degrees":"90"},         # string, not number -> invalid
+            {"type":"rotateZ","radians":0.7,"degrees":33},   # degrees wins
+            {"type":"scale","Z":2.0},                  # others default to 1
+            {"type":"scale"},                           # invalid -> NOP
+            {"type":"scaleUniform"},                    # invalid
+            {"type":"scaleUniform","scale":0.3},
+            {"type":"shear","X":1},                    # unknown type
+            {"type":"translate","X":-0.0,"Y":1e-30,"Z":1e20},
+            {"type":"rotateX","degrees":720.5},
+        ]))
+    return out
+def _odd_scene(rng, d):
+    images=[]
+    rows=[bytes(rng.randrange(256) for _ in range(4*3)) for _ in range(3)]
+    p=os.path.join(d,"t.png"); open(p,"wb").write(_png(4,3,2,8,rows)); images.append(p)
+    prims=[]
+    for _ in range(rng.randrange(1,6)):
+        s={"type":"sphere"}
+        if rng.random()<0.8: s["radius"]=rng.choice([0.5,1,"2",-1.0,0])
+        if rng.random()<0.9: s["instances"]=[{"transforms":_odd_transforms(rng)} if rng.random()<0.8 else {} for _ in range(rng.randrange(0,3))]
+        r=rng.random()
+        if r<0.3: s["material"]=rng.choice([{"type":"diffuse"},{"type":"mix"},{"type":"mix","A":{"type":"diffuse","color":[1,0,0]}},{"type":"add","A":{"type":"metal"},"B":{"type":"metal"}},
+                                            {"type":"unknown"},{"no":"type"},{"type":"emissive","color":{"type":"checkerboard","size":3},"strength":{"type":"checkerboard","size":2}},
+                                            {"type":"glass","color":[1,1,1],"roughness":{"path":images[0]},"IOR":{"r":1,"g":1,"b":1}},
+                                            {"type":"plastic"},{"type":"transparent"},{"type":"metal","color":"t.png"},{"type":"diffuse","color":{"path":"nonexistent.png"}},
+                                            {"type":"diffuse","color":{"type":"image","path":images[0],"transform":False,"lerp":True}}])
+        else:
+            if rng.random()<0.8: s["bsdf"]=rng.choice(["lambertian","metal","glass","plastic","emissive","EMISSIVE",5])
+            if rng.random()<0.8: s["color"]=rng.choice([[1,0.5],[0.1,0.2,0.3,0.4],{"r":0.5},{"blackbody":2500},{"blackbody":"x","g":0.5},[]])
+            if rng.random()<0.5: s["intensity"]=rng.choice([2,"3",0])
+            if rng.random()<0.5: s["roughness"]=rng.choice([0.25,"0.5",-1])
+            if rng.random()<0.5: s["IOR"]=rng.choice([1.5,"1.5"])
+        prims.append(s)
+    prims.append({"type":"cube"}) if rng.random()<0.3 else None
+    cam={}
+    if rng.random()<0.8: cam[rng.choice(["FOV","fov","Fov"])]=rng.choice([-5,0,45,181,90.5])
+    if rng.random()<0.6: cam["focalDistance"]=rng.choice([-1,0,3.5])
+    if rng.random()<0.6: cam["fstops"]=rng.choice([-1,0,2.8])
+    if rng.random()<0.7: cam["transforms"]=_odd_transforms(rng)
+    ren={}
+    for k,vals in (("samples",[0,-1,3,2.7]),("bounces",[-2,0,7]),("width",[17,0.0,64]),("height",[9,33]),("tileWidth",[0,5]),("tileHeight",[-3,7]),("threads",[0,-1,3]),("tileOrder",["random","normal","xyz",3])):
+        if rng.random()<0.7: ren[rng.choice([k,k.upper(),k.capitalize()])]=rng.choice(vals)
+    amb=rng.choice([{}, {"offset":90}, {"down":[0,0,0]}, {"down":[1,1,1],"up":[0,0,1],"offset":"5"}, {"hdr":5,"up":[1,1,1],"down":{"blackbody":6000}}])
+    sc={"camera":cam,"scene":{"ambientColor":amb,"primitives":prims}}
+    if rng.random()<0.9: sc["renderer"]=ren
+    return sc
+
+
+def test_odd_inputs_against_live_reference(tmp_path, monkeypatch):
+    """Defaults, clamps and fallbacks of the JSON dialect (sceneloader.c): 60 scenes made of values the loader has to
+    tolerate — strings where numbers belong, missing radius/color/bsdf, lower-case keys, transforms without arguments,
+    mix/add nodes with missing inputs, unknown node and primitive types, textures that do not exist."""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/cray_ref_strict is only built where /root/reference exists")
+    compared = 0
+    for seed in range(60):
+        rng = random.Random(777 + seed)
+        d = str(tmp_path / ("odd%d" % seed))
+        os.makedirs(d)
+        sc = _odd_scene(rng, d)
+        if any(k.lower() in ("width", "height") and v == 0 for k, v in sc.get("renderer", {}).items()):
+            continue                                         # zero-sized image: the reference divides by zero, the loader reports it
+        open(os.path.join(d, "s.json"), "w").write(json.dumps(sc))
+        r = subprocess.run([REF, "export", "s.json", "0", "0", "0", "0", "ref.crscene"], cwd=d, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, errors="replace", timeout=60)
+        assert r.returncode == 0, (seed, r.stdout[-500:])
+        monkeypatch.chdir(d)
+        mine = crscene.load_json("s.json")
+        assert_same_scene(mine, load_crscene(os.path.join(d, "ref.crscene")))
+        crscene.free(mine)
+        compared += 1
+    assert compared >= 40
+
+
 # ------------------------------------------------------------------------------------------------ GPU end to end
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["g_nodes", "g_meshmat", "g_single"])
