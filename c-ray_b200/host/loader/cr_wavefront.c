@@ -117,6 +117,12 @@ int crl_load_texture(struct crl_ctx *c, const char *path_in) {
 }
 
 /* ---- MTL --------------------------------------------------------------------------------------------- */
+static void free_materials(struct crl_material *set, int count) {
+	if (!set) return;
+	for (int i = 0; i < count; ++i) free(set[i].name);
+	free(set);
+}
+
 static int next_float(struct toks *t, float *out) {
 	const char *s = toks_next(t);
 	if (!s) return -1;
@@ -185,7 +191,7 @@ static int load_mtl(struct crl_ctx *c, const char *path, struct crl_material **o
 	free(text);
 	if (rc) {
 		snprintf(c->err, sizeof(c->err), "malformed MTL file %s", path);
-		free(mats);
+		free_materials(mats, total);
 		return -1;
 	}
 	*out = mats;
@@ -396,8 +402,11 @@ int crl_load_obj(struct crl_ctx *c, const char *path, struct crl_mesh *out) {
 					int n = 0, mrc = load_mtl(c, p, &set, &n);
 					free(p);
 					if (mrc < 0) rc = -3;
-					else if (mrc == 0) { materials = set; material_count = n; }
-					else { materials = NULL; material_count = 0; }
+					else {
+						free_materials(materials, material_count);          /* a later mtllib replaces the set (wavefront.c:213) */
+						materials = mrc == 0 ? set : NULL;
+						material_count = mrc == 0 ? n : 0;
+					}
 				}
 			} else {
 				current_material = find_material(materials, material_count, arg);
@@ -422,6 +431,7 @@ int crl_load_obj(struct crl_ctx *c, const char *path, struct crl_mesh *out) {
 		if (rc == -2) snprintf(c->err, sizeof(c->err), "%s: faces must be triangles or quads written v/vt/vn or v//vn", path);
 		else if (rc == -1) snprintf(c->err, sizeof(c->err), "%s: malformed OBJ statement", path);
 		free(J.vertices); free(J.texcoords); free(J.normals); free(J.polys);
+		free_materials(materials, material_count);
 		return -1;
 	}
 

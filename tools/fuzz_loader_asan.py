@@ -47,7 +47,7 @@ for seed in range(200):
     else:
         i=rng.randrange(len(data)); j=min(len(data),i+rng.randrange(1,200)); del data[i:j]
     open(p,'wb').write(bytes(data))
-    r=subprocess.run([EXE,'fuzz.json'],cwd=d,stdout=subprocess.PIPE,stderr=subprocess.PIPE,text=True,errors='replace',timeout=120,env=dict(os.environ,ASAN_OPTIONS='detect_leaks=0'))
+    r=subprocess.run([EXE,'fuzz.json'],cwd=d,stdout=subprocess.PIPE,stderr=subprocess.PIPE,text=True,errors='replace',timeout=120,env=dict(os.environ,ASAN_OPTIONS='detect_leaks=1'))
     runs+=1
     if 'AddressSanitizer' in r.stderr or 'runtime error' in r.stderr or r.returncode not in (0,):
         fails+=1; print('CORRUPT',seed,f,mode,'rc',r.returncode, r.stderr[-1200:])
