@@ -107,3 +107,24 @@ def test_bundled_scenes_against_reference_framebuffers(name, W, H, spp, b):
     img = sc.render(threads=os.cpu_count())
     assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
     sc.close()
+
+
+@pytest.mark.parametrize("name,W,H,spp,b", [("hdr", 1920, 1080, 2, 32), ("venus", 2560, 1600, 1, 25), ("refraction", 1920, 1080, 1, 512)])
+def test_full_size_frames_bit_exact_against_live_reference(name, W, H, spp, b, tmp_path):
+    """BASELINE.json configs C2 / C4 / C3 at their full image sizes (few spp): the strict reference build, run here, and the
+    oracle produce the same fp32 frame bit for bit.  (The GPU suite then checks bands of these frames against the oracle.)"""
+    import subprocess
+    from conftest import ROOT
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "cray_ref_strict")
+    scene = os.path.join(BUILT, name + ".crscene")
+    if not (os.path.exists(ref_exe) and os.path.exists(scene)):
+        pytest.skip("needs oracle/_ref (built where /root/reference exists)")
+    out = str(tmp_path / "ref.f32")
+    r = subprocess.run([ref_exe, "render", os.path.join("input", name + ".json"), str(W), str(H), str(spp), str(b), str(os.cpu_count() or 1), "0", "0", out],
+                       cwd=os.path.join(ROOT, "oracle", "_ref"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1000:]
+    ref = np.fromfile(out, dtype=np.float32).reshape(H, W, 3)
+    sc = O.OracleScene(scene, W, H, spp, b)
+    img = sc.render(threads=os.cpu_count())
+    assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+    sc.close()
