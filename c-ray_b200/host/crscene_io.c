@@ -88,7 +88,7 @@ int crscene_load(struct crs_scene *out, const char *path) {
 	size_t off = header_bytes();
 	void *ptrs[14];
 	for (int i = 0; i < 14; ++i) {
-		if (off + sec[i].bytes > (size_t)size) { free(buf); memset(out, 0, sizeof(*out)); return -6; }
+		if (off > (size_t)size || sec[i].bytes > (size_t)size - off) {   /* overflow-safe: counts come from the file */ free(buf); memset(out, 0, sizeof(*out)); return -6; }
 		ptrs[i] = sec[i].bytes ? buf + off : NULL;
 		off += align16(sec[i].bytes);
 	}
