@@ -655,7 +655,11 @@ extern "C" int crgpu_render_tiles(crgpu_scene *s, const int *rects, int nrects, 
 			CU(cudaMalloc((void **)&s->pixels, px.size() * sizeof(uint32_t)));
 			s->pixel_cap = px.size();
 		}
-		CU(cudaMemcpy(s->pixels, px.data(), px.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		/* on the scene's own stream, then wait: a plain cudaMemcpy from pageable memory runs on the legacy stream and may
+		 * return while the last DMA chunk is still in flight; kernels on a NON-BLOCKING stream are not ordered after it,
+		 * so the first k_generate of this tile set could read the previous set's coordinates */
+		CU(cudaMemcpyAsync(s->pixels, px.data(), px.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+		CU(cudaStreamSynchronize(s->stream));
 		s->pixel_key.swap(key);
 	}
 	TileDesc td;
