@@ -189,6 +189,23 @@ int cr_image_decode_hdr(const unsigned char *buf, size_t len, struct cr_image *o
 	return 0;
 }
 
+/* Cheap plausibility check used before a decode is handed to a background thread: 1 when the header looks like something
+ * the decoders accept (a full decode can still fail later, e.g. on a corrupt deflate stream). */
+int cr_image_probe(const unsigned char *buf, size_t len) {
+	if (cr_path_is_hdr(buf, len)) return 1;
+	static const unsigned char sig[8] = { 0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n' };
+	if (len < 8 + 12 + 13 || memcmp(buf, sig, 8) || memcmp(buf + 12, "IHDR", 4) || be32(buf + 8) < 13) return 0;
+	const unsigned char *d = buf + 16;
+	const int depth = d[8], ctype = d[9], interlace = d[12];
+	const int src_n = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+	if (!be32(d) || !be32(d + 4) || interlace || !src_n) return 0;
+	return depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3));
+}
+
+int cr_image_decode(const unsigned char *buf, size_t len, struct cr_image *out) {
+	return cr_path_is_hdr(buf, len) ? cr_image_decode_hdr(buf, len, out) : cr_image_decode_png(buf, len, out);
+}
+
 int cr_image_load(const char *path, struct cr_image *out) {
 	memset(out, 0, sizeof *out);
 	FILE *f = fopen(path, "rb");
@@ -199,7 +216,7 @@ int cr_image_load(const char *path, struct cr_image *out) {
 	unsigned char *buf = malloc(n > 0 ? (size_t)n : 1);
 	if (!buf || fread(buf, 1, (size_t)n, f) != (size_t)n) { fclose(f); free(buf); return -101; }
 	fclose(f);
-	int rc = cr_path_is_hdr(buf, (size_t)n) ? cr_image_decode_hdr(buf, (size_t)n, out) : cr_image_decode_png(buf, (size_t)n, out);
+	int rc = cr_image_decode(buf, (size_t)n, out);
 	free(buf);
 	return rc;
 }

@@ -20,3 +20,5 @@ int cr_image_load(const char *path, struct cr_image *out);
 int cr_image_decode_png(const unsigned char *buf, size_t len, struct cr_image *out);
 int cr_image_decode_hdr(const unsigned char *buf, size_t len, struct cr_image *out);
 int cr_path_is_hdr(const unsigned char *buf, size_t len);
+int cr_image_decode(const unsigned char *buf, size_t len, struct cr_image *out);   /* picks the decoder from the content */
+int cr_image_probe(const unsigned char *buf, size_t len);                          /* 1 = header plausible */

@@ -69,6 +69,11 @@ struct crl_ctx {
 
 	struct cr_image *textures;    /* every successful loadTexture() call, in call order */
 	int texture_count;
+	/* texture files are decoded on background threads while parsing and BVH construction go on (a 2048x2048 PNG inflates
+	 * for ~0.1 s on one core); a decode that fails after its header looked fine makes the whole load restart synchronously,
+	 * because a missing texture changes the node graph (image.c:51: NULL texture -> no image node) */
+	struct crl_tex_job **tex_jobs;
+	int async_textures, async_failed;
 
 	struct crl_node *nodes;       /* creation order */
 	int node_count, node_cap;
@@ -82,6 +87,7 @@ struct crl_ctx {
 /* cr_wavefront.c */
 int crl_load_obj(struct crl_ctx *c, const char *path, struct crl_mesh *out);      /* 0 ok, 1 = "no mesh" (skip), <0 error */
 int crl_load_texture(struct crl_ctx *c, const char *path);                        /* handle or -1 */
+void crl_textures_join(struct crl_ctx *c);                                        /* waits for background decodes; sets c->async_failed */
 
 /* cr_bvh_build.c */
 typedef void (*crl_bbox_fn)(void *user, unsigned i, bbox3 *bbox, vec3 *center);

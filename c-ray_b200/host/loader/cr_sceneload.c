@@ -571,6 +571,8 @@ static int flatten(struct crl_ctx *c, const struct crs_prefs *prefs, const struc
 
 /* ---- entry point ------------------------------------------------------------------------------------------ */
 static void ctx_free(struct crl_ctx *c) {
+	crl_textures_join(c);                                  /* error paths: no decode thread may outlive the context */
+	free(c->tex_jobs);
 	for (int m = 0; m < c->mesh_count; ++m) {
 		struct crl_mesh *mesh = &c->meshes[m];
 		for (int k = 0; k < mesh->material_count; ++k) free(mesh->materials[k].name);
@@ -582,6 +584,7 @@ static void ctx_free(struct crl_ctx *c) {
 }
 
 static int load_text(struct crs_scene *out, const char *text, const char *asset_path, const char *what, struct crloader_output *output);
+static int load_text_mode(struct crs_scene *out, const char *text, const char *asset_path, const char *what, struct crloader_output *output, int async);
 
 int crloader_load_json(struct crs_scene *out, const char *json_path) {
 	g_err[0] = '\0';
@@ -615,6 +618,13 @@ static void parse_output(const struct crj *d, struct crloader_output *o) {   /* 
 }
 
 static int load_text(struct crs_scene *out, const char *text, const char *asset_path, const char *what, struct crloader_output *output) {
+	const int async = crl_thread_count() > 1 && !getenv("CRLOADER_SYNC_TEXTURES");
+	int rc = load_text_mode(out, text, asset_path, what, output, async);
+	if (rc == -100) rc = load_text_mode(out, text, asset_path, what, output, 0);   /* a background decode failed late: redo in order */
+	return rc;
+}
+
+static int load_text_mode(struct crs_scene *out, const char *text, const char *asset_path, const char *what, struct crloader_output *output, int async) {
 	struct crj *json = crj_parse(text);
 	if (!json) { snprintf(g_err, sizeof(g_err), "%s: JSON syntax error", what); return -3; }
 	if (output) parse_output(crj_get(json, "renderer"), output);
@@ -623,6 +633,7 @@ static int load_text(struct crs_scene *out, const char *text, const char *asset_
 	memset(&ctx, 0, sizeof(ctx));
 	ctx.background = -1;
 	ctx.asset_path = strdup(asset_path);
+	ctx.async_textures = async;
 	struct crs_prefs prefs;
 	struct crs_camera cam;
 	struct crs_bvh_node *top_nodes = NULL;
@@ -677,6 +688,8 @@ static int load_text(struct crs_scene *out, const char *text, const char *asset_
 		uint32_t ty = (prefs.image_height + prefs.tile_height - 1) / prefs.tile_height;
 		if (tx * ty < prefs.thread_count) prefs.thread_count = tx * ty;
 	}
+	crl_textures_join(&ctx);
+	if (ctx.async_failed) { rc = -100; goto done; }
 	rc = flatten(&ctx, &prefs, &cam, top_nodes, top_count, top_prims, out) ? -5 : 0;
 done:
 	free(top_nodes); free(top_prims);

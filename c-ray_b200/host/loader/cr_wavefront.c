@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <libgen.h>
+#include <pthread.h>
 
 #define LINE_MAX_BYTES 2048
 
@@ -100,11 +101,45 @@ static char *concat(const char *a, const char *b) {
 static int starts_with(const char *prefix, const char *s) { return strncmp(prefix, s, strlen(prefix)) == 0; }
 
 /* ---- textures ---------------------------------------------------------------------------------------- */
+struct crl_tex_job { pthread_t thread; unsigned char *buf; size_t len; struct cr_image img; int rc; };
+
+static void *tex_decode_thread(void *arg) {
+	struct crl_tex_job *j = arg;
+	j->rc = cr_image_decode(j->buf, j->len, &j->img);
+	free(j->buf);
+	j->buf = NULL;
+	return NULL;
+}
+
+void crl_textures_join(struct crl_ctx *c) {
+	for (int i = 0; i < c->texture_count; ++i) {
+		struct crl_tex_job *j = c->tex_jobs ? c->tex_jobs[i] : NULL;
+		if (!j) continue;
+		pthread_join(j->thread, NULL);
+		if (j->rc) { c->async_failed = 1; free(j->img.data); }
+		else c->textures[i] = j->img;
+		free(j);
+		c->tex_jobs[i] = NULL;
+	}
+}
+
 int crl_load_texture(struct crl_ctx *c, const char *path_in) {
 	char *path = strdup(path_in);
 	path[strcspn(path, "\n")] = 0;                      /* textureloader.c:58 */
+	size_t len = 0;
+	unsigned char *buf = (unsigned char *)read_file(path, &len);
 	struct cr_image img;
-	int rc = cr_image_load(path, &img);
+	memset(&img, 0, sizeof img);
+	struct crl_tex_job *job = NULL;
+	int rc = buf ? 0 : -100;
+	if (buf && c->async_textures && cr_image_probe(buf, len)) {
+		job = calloc(1, sizeof *job);
+		if (job) {
+			job->buf = buf; job->len = len;
+			if (pthread_create(&job->thread, NULL, tex_decode_thread, job) != 0) { free(job); job = NULL; }
+		}
+	}
+	if (buf && !job) { rc = cr_image_decode(buf, len, &img); free(buf); }
 	if (rc) {
 		fprintf(stderr, "cr_loader: cannot decode texture \"%s\" (%d)\n", path, rc);
 		free(path);
@@ -112,7 +147,9 @@ int crl_load_texture(struct crl_ctx *c, const char *path_in) {
 	}
 	free(path);
 	c->textures = realloc(c->textures, (size_t)(c->texture_count + 1) * sizeof(*c->textures));
+	c->tex_jobs = realloc(c->tex_jobs, (size_t)(c->texture_count + 1) * sizeof(*c->tex_jobs));
 	c->textures[c->texture_count] = img;
+	c->tex_jobs[c->texture_count] = job;
 	return c->texture_count++;
 }
 
