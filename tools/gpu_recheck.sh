@@ -24,5 +24,7 @@ print(f"-j {n}: identical to -j 1: {len(bad) == 0}" + ("" if len(bad) == 0 else 
 PY
   done
 fi
+echo "== full-config RMSE (hdr 1920x1080 1000 spp: GPU vs oracle on all host cores; minutes)"
+timeout 900 python tools/full_rmse.py 2>&1 | tail -1
 echo "== bench (short)"
 timeout 600 python bench.py --steps 2 --warmup 3 --spp 200 --no-cpu-baseline 2>/dev/null | tail -1 | cut -c1-600
