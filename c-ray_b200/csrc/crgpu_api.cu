@@ -18,6 +18,8 @@
 #include <cstdarg>
 #include <vector>
 #include <queue>
+#include <thread>
+#include <mutex>
 
 static thread_local char g_err[512] = "";
 
@@ -155,7 +157,32 @@ static int check_bsdf(const crs_scene *f, int idx, int add_level, int guard, boo
 }
 
 /* ---- BVH re-layout: reference nodes (bvh.c:37-42) -> BFS-ordered PairNodes ---------------------------------------- */
-static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNode> &pairs, DevBvh &out, uint32_t slot_offset) {
+/* errors raised on worker threads (fail() writes a thread-local buffer): first one wins, reported by the caller */
+struct HostError {
+	std::mutex lock;
+	int code = 0;
+	char msg[256] = "";
+	int set(int c, const char *m) { std::lock_guard<std::mutex> g(lock); if (!code) { code = c; snprintf(msg, sizeof msg, "%s", m); } return c; }
+};
+
+/* fn(lo, hi) over [0, n) on a few host threads (CRGPU_HOST_THREADS, default min(hardware, 16)); small n stays inline */
+template <class F>
+static void host_parallel_for(uint32_t n, F fn) {
+	static const unsigned want = [] {
+		const char *e = getenv("CRGPU_HOST_THREADS");
+		unsigned t = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
+		return t < 1u ? 1u : (t > 16u ? 16u : t);
+	}();
+	const unsigned threads = n < 16384u ? 1u : want;
+	if (threads <= 1u) { fn(0u, n); return; }
+	std::vector<std::thread> pool;
+	for (unsigned k = 1; k < threads; ++k)
+		pool.emplace_back(fn, (uint32_t)((uint64_t)n * k / threads), (uint32_t)((uint64_t)n * (k + 1) / threads));
+	fn(0u, (uint32_t)((uint64_t)n / threads));
+	for (auto &t : pool) t.join();
+}
+
+static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNode> &pairs, DevBvh &out, uint32_t slot_offset, HostError *err) {
 	memset(&out, 0, sizeof out);
 	out.pair_offset = (uint32_t)pairs.size();
 	out.pair_end = out.pair_offset;
@@ -171,37 +198,42 @@ static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNod
 	}
 	/* BFS over internal nodes; pair index = BFS rank */
 	std::vector<uint32_t> order;            /* reference node index of each internal node, BFS order */
+	order.reserve(b.node_count / 2 + 1);
 	std::vector<uint32_t> rank(b.node_count, 0xffffffffu);
 	order.push_back(0);
 	rank[0] = 0;
 	for (size_t head = 0; head < order.size(); ++head) {
 		const crs_bvh_node &n = nodes[order[head]];
-		if (n.prim_count_leaf & CRS_BVH_LEAF_BIT) return fail(CRGPU_ERR_BAD_ARGUMENT, "BVH root/internal node is a leaf");
+		if (n.prim_count_leaf & CRS_BVH_LEAF_BIT) return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH root/internal node is a leaf");
 		const uint32_t fc = n.first_child_or_prim;
-		if (fc + 1 >= b.node_count) return fail(CRGPU_ERR_BAD_ARGUMENT, "BVH child index out of range");
+		if (fc + 1 >= b.node_count) return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH child index out of range");
 		for (uint32_t k = 0; k < 2; ++k) {
 			const crs_bvh_node &c = nodes[fc + k];
 			if (!(c.prim_count_leaf & CRS_BVH_LEAF_BIT)) {
-				if (rank[fc + k] != 0xffffffffu) return fail(CRGPU_ERR_BAD_ARGUMENT, "BVH is not a tree");
+				if (rank[fc + k] != 0xffffffffu) return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH is not a tree");
 				rank[fc + k] = (uint32_t)order.size();
 				order.push_back(fc + k);
 			}
 		}
 	}
-	for (size_t r = 0; r < order.size(); ++r) {
-		const crs_bvh_node &n = nodes[order[r]];
-		const uint32_t fc = n.first_child_or_prim;
-		PairNode p;
-		memset(&p, 0, sizeof p);
-		const crs_bvh_node &l = nodes[fc], &rr = nodes[fc + 1];
-		memcpy(p.lb, l.bounds, sizeof p.lb);
-		memcpy(p.rb, rr.bounds, sizeof p.rb);
-		if (l.prim_count_leaf & CRS_BVH_LEAF_BIT) { p.lref = l.first_child_or_prim; p.lmeta = CRG_LEAF_BIT | (l.prim_count_leaf & CRS_BVH_COUNT_MASK); }
-		else { p.lref = rank[fc]; p.lmeta = 0; }
-		if (rr.prim_count_leaf & CRS_BVH_LEAF_BIT) { p.rref = rr.first_child_or_prim; p.rmeta = CRG_LEAF_BIT | (rr.prim_count_leaf & CRS_BVH_COUNT_MASK); }
-		else { p.rref = rank[fc + 1]; p.rmeta = 0; }
-		pairs.push_back(p);
-	}
+	const size_t first = pairs.size();
+	pairs.resize(first + order.size());
+	host_parallel_for((uint32_t)order.size(), [&](uint32_t lo, uint32_t hi) {
+		for (uint32_t r = lo; r < hi; ++r) {
+			const crs_bvh_node &n = nodes[order[r]];
+			const uint32_t fc = n.first_child_or_prim;
+			PairNode p;
+			memset(&p, 0, sizeof p);
+			const crs_bvh_node &l = nodes[fc], &rr = nodes[fc + 1];
+			memcpy(p.lb, l.bounds, sizeof p.lb);
+			memcpy(p.rb, rr.bounds, sizeof p.rb);
+			if (l.prim_count_leaf & CRS_BVH_LEAF_BIT) { p.lref = l.first_child_or_prim; p.lmeta = CRG_LEAF_BIT | (l.prim_count_leaf & CRS_BVH_COUNT_MASK); }
+			else { p.lref = rank[fc]; p.lmeta = 0; }
+			if (rr.prim_count_leaf & CRS_BVH_LEAF_BIT) { p.rref = rr.first_child_or_prim; p.rmeta = CRG_LEAF_BIT | (rr.prim_count_leaf & CRS_BVH_COUNT_MASK); }
+			else { p.rref = rank[fc + 1]; p.rmeta = 0; }
+			pairs[first + r] = p;
+		}
+	});
 	out.pair_end = (uint32_t)pairs.size();
 	return CRGPU_OK;
 }
@@ -293,7 +325,9 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 		mats[i] = d;
 	}
 
-	/* BVHs → pair nodes; triangles in leaf order */
+	/* BVHs → pair nodes; triangles in leaf order; per-poly shading records.  The three products are independent once the
+	 * slot offsets are known, and every element is computed from the flat scene alone, so they are filled by index on a
+	 * few host threads (the upload bytes do not depend on the thread count).  This is most of crgpu_scene_create's time. */
 	std::vector<PairNode> pairs;
 	std::vector<DevBvh> bvhs(f->bvh_count);
 	std::vector<PackedTri> tris;
@@ -304,83 +338,113 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 		if (f->meshes[m].bvh >= f->bvh_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "mesh bvh index out of range"); }
 		mesh_of_bvh[f->meshes[m].bvh] = m;
 	}
+	std::vector<uint32_t> slot_off(f->bvh_count, 0u);      /* first triangle slot of every mesh BVH (0 for the top level) */
+	uint64_t total_slots = 0;
 	for (uint32_t b = 0; b < f->bvh_count; ++b) {
 		const crs_bvh &src = f->bvhs[b];
 		if ((uint64_t)src.node_offset + src.node_count > f->bvh_node_count || (uint64_t)src.prim_offset + src.prim_count > f->prim_index_count) {
 			crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u ranges out of bounds", b);
 		}
-		if (b == f->top_bvh) {
-			FAIL_IF(build_pairs(f, src, pairs, bvhs[b], (uint32_t)top_prims.size()));
-			for (uint32_t i = 0; i < src.prim_count; ++i) {
-				const int32_t inst = f->prim_indices[src.prim_offset + i];
-				if (inst < 0 || (uint32_t)inst >= f->instance_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "top-level prim index out of range"); }
-				top_prims.push_back(inst);
-			}
-			continue;
-		}
-		const uint32_t m = mesh_of_bvh[b];
-		if (m == 0xffffffffu) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u belongs to no mesh", b); }
-		const crs_mesh &mesh = f->meshes[m];
-		FAIL_IF(build_pairs(f, src, pairs, bvhs[b], (uint32_t)tris.size()));
-		for (uint32_t i = 0; i < src.prim_count; ++i) {
-			const int32_t local = f->prim_indices[src.prim_offset + i];
-			if (local < 0 || (uint32_t)local >= mesh.poly_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "prim index out of range"); }
-			const uint32_t poly = mesh.poly_offset + (uint32_t)local;
-			const crs_poly &p = f->polys[poly];
-			for (int k = 0; k < 3; ++k)
-				if (p.v[k] < 0 || (uint32_t)p.v[k] >= f->vertex_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "vertex index out of range"); }
-			float v0[3], v1[3], v2[3];
-			f3(v0, f->vertices, (size_t)p.v[0]); f3(v1, f->vertices, (size_t)p.v[1]); f3(v2, f->vertices, (size_t)p.v[2]);
-			PackedTri t;
-			/* poly.c:20-22 — plain fp32 ops; this TU is compiled without contraction on the host side */
-			for (int k = 0; k < 3; ++k) { t.v0[k] = v0[k]; t.e1[k] = v0[k] - v1[k]; t.e2[k] = v2[k] - v0[k]; }
-			volatile float m0 = t.e1[1] * t.e2[2], m1 = t.e1[2] * t.e2[1], m2 = t.e1[2] * t.e2[0], m3 = t.e1[0] * t.e2[2],
-						   m4 = t.e1[0] * t.e2[1], m5 = t.e1[1] * t.e2[0];
-			t.n[0] = m0 - m1; t.n[1] = m2 - m3; t.n[2] = m4 - m5;
-			tris.push_back(t);
-			slot_poly.push_back(poly);
-		}
+		if (b == f->top_bvh) continue;
+		if (mesh_of_bvh[b] == 0xffffffffu) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u belongs to no mesh", b); }
+		slot_off[b] = (uint32_t)total_slots;
+		total_slots += src.prim_count;
 	}
-
-	/* per-poly shading records */
-	std::vector<ShadePoly> spolys(f->poly_count);
+	if (total_slots > 0xffffffffull) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_UNSUPPORTED, "more than 2^32 triangle slots"); }
 	for (uint32_t m = 0; m < f->mesh_count; ++m) {
 		const crs_mesh &mesh = f->meshes[m];
 		if ((uint64_t)mesh.poly_offset + mesh.poly_count > f->poly_count || (uint64_t)mesh.material_offset + mesh.material_count > f->material_count) {
 			crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "mesh %u ranges out of bounds", m);
 		}
-		for (uint32_t i = 0; i < mesh.poly_count; ++i) {
-			const crs_poly &p = f->polys[mesh.poly_offset + i];
-			ShadePoly sp;
-			memset(&sp, 0, sizeof sp);
-			bool has_n = p.has_normals != 0;
-			for (int k = 0; k < 3 && has_n; ++k) if (p.n[k] < 0 || (uint32_t)p.n[k] >= f->normal_count) has_n = false;
-			if (has_n) {
-				f3(sp.n0, f->normals, (size_t)p.n[0]); f3(sp.n1, f->normals, (size_t)p.n[1]); f3(sp.n2, f->normals, (size_t)p.n[2]);
-			} else if (p.has_normals) {
-				crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "normal index out of range");
-			} else {
-				/* geometric normal e1 x e2 (poly.c:22,46), same operations as above */
-				float v0[3], v1[3], v2[3], e1[3], e2[3];
-				f3(v0, f->vertices, (size_t)p.v[0]); f3(v1, f->vertices, (size_t)p.v[1]); f3(v2, f->vertices, (size_t)p.v[2]);
-				for (int k = 0; k < 3; ++k) { e1[k] = v0[k] - v1[k]; e2[k] = v2[k] - v0[k]; }
-				volatile float m0 = e1[1] * e2[2], m1 = e1[2] * e2[1], m2 = e1[2] * e2[0], m3 = e1[0] * e2[2], m4 = e1[0] * e2[1], m5 = e1[1] * e2[0];
-				sp.n0[0] = m0 - m1; sp.n0[1] = m2 - m3; sp.n0[2] = m4 - m5;
-			}
-			bool has_uv = mesh.texcoord_count != 0 && p.t[0] != -1;                          /* instance.c:151-153 */
-			if (has_uv) {
-				for (int k = 0; k < 3; ++k)
-					if (p.t[k] < 0 || (uint32_t)p.t[k] >= f->texcoord_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "texcoord index out of range"); }
-				sp.t0[0] = f->texcoords[2 * (size_t)p.t[0]]; sp.t0[1] = f->texcoords[2 * (size_t)p.t[0] + 1];
-				sp.t1[0] = f->texcoords[2 * (size_t)p.t[1]]; sp.t1[1] = f->texcoords[2 * (size_t)p.t[1] + 1];
-				sp.t2[0] = f->texcoords[2 * (size_t)p.t[2]]; sp.t2[1] = f->texcoords[2 * (size_t)p.t[2] + 1];
-			}
-			if (p.material >= mesh.material_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "poly material index out of range"); }
-			sp.material = mesh.material_offset + p.material;
-			sp.flags = (has_n ? 1u : 0u) | (has_uv ? 2u : 0u);
-			spolys[mesh.poly_offset + i] = sp;
-		}
 	}
+	tris.resize((size_t)total_slots);
+	slot_poly.resize((size_t)total_slots);
+	std::vector<ShadePoly> spolys(f->poly_count);
+	HostError herr;
+
+	/* (1) pair nodes of every BVH, in BVH order (sequential: each BVH appends behind the previous one) */
+	std::thread pair_thread([&] {
+		for (uint32_t b = 0; b < f->bvh_count; ++b) {
+			const crs_bvh &src = f->bvhs[b];
+			if (build_pairs(f, src, pairs, bvhs[b], b == f->top_bvh ? 0u : slot_off[b], &herr)) return;
+			if (b != f->top_bvh) continue;
+			for (uint32_t i = 0; i < src.prim_count; ++i) {
+				const int32_t inst = f->prim_indices[src.prim_offset + i];
+				if (inst < 0 || (uint32_t)inst >= f->instance_count) { herr.set(CRGPU_ERR_BAD_ARGUMENT, "top-level prim index out of range"); return; }
+				top_prims.push_back(inst);
+			}
+		}
+	});
+
+	/* (2) triangles in leaf order */
+	for (uint32_t b = 0; b < f->bvh_count; ++b) {
+		if (b == f->top_bvh) continue;
+		const crs_bvh &src = f->bvhs[b];
+		const crs_mesh &mesh = f->meshes[mesh_of_bvh[b]];
+		const uint32_t base = slot_off[b];
+		host_parallel_for(src.prim_count, [&](uint32_t lo, uint32_t hi) {
+			for (uint32_t i = lo; i < hi; ++i) {
+				const int32_t local = f->prim_indices[src.prim_offset + i];
+				if (local < 0 || (uint32_t)local >= mesh.poly_count) { herr.set(CRGPU_ERR_BAD_ARGUMENT, "prim index out of range"); return; }
+				const uint32_t poly = mesh.poly_offset + (uint32_t)local;
+				const crs_poly &p = f->polys[poly];
+				for (int k = 0; k < 3; ++k)
+					if (p.v[k] < 0 || (uint32_t)p.v[k] >= f->vertex_count) { herr.set(CRGPU_ERR_BAD_ARGUMENT, "vertex index out of range"); return; }
+				float v0[3], v1[3], v2[3];
+				f3(v0, f->vertices, (size_t)p.v[0]); f3(v1, f->vertices, (size_t)p.v[1]); f3(v2, f->vertices, (size_t)p.v[2]);
+				PackedTri t;
+				/* poly.c:20-22 — plain fp32 ops; this TU is compiled without contraction on the host side */
+				for (int k = 0; k < 3; ++k) { t.v0[k] = v0[k]; t.e1[k] = v0[k] - v1[k]; t.e2[k] = v2[k] - v0[k]; }
+				volatile float m0 = t.e1[1] * t.e2[2], m1 = t.e1[2] * t.e2[1], m2 = t.e1[2] * t.e2[0], m3 = t.e1[0] * t.e2[2],
+							   m4 = t.e1[0] * t.e2[1], m5 = t.e1[1] * t.e2[0];
+				t.n[0] = m0 - m1; t.n[1] = m2 - m3; t.n[2] = m4 - m5;
+				tris[(size_t)base + i] = t;
+				slot_poly[(size_t)base + i] = poly;
+			}
+		});
+	}
+
+	/* (3) per-poly shading records (meshes in order: should two meshes claim the same polygons, the later one wins as before) */
+	for (uint32_t m = 0; m < f->mesh_count; ++m) {
+		const crs_mesh &mesh = f->meshes[m];
+		host_parallel_for(mesh.poly_count, [&](uint32_t lo, uint32_t hi) {
+			for (uint32_t i = lo; i < hi; ++i) {
+				const crs_poly &p = f->polys[mesh.poly_offset + i];
+				ShadePoly sp;
+				memset(&sp, 0, sizeof sp);
+				bool has_n = p.has_normals != 0;
+				for (int k = 0; k < 3 && has_n; ++k) if (p.n[k] < 0 || (uint32_t)p.n[k] >= f->normal_count) has_n = false;
+				if (has_n) {
+					f3(sp.n0, f->normals, (size_t)p.n[0]); f3(sp.n1, f->normals, (size_t)p.n[1]); f3(sp.n2, f->normals, (size_t)p.n[2]);
+				} else if (p.has_normals) {
+					herr.set(CRGPU_ERR_BAD_ARGUMENT, "normal index out of range"); return;
+				} else {
+					/* geometric normal e1 x e2 (poly.c:22,46), same operations as above */
+					for (int k = 0; k < 3; ++k)
+						if (p.v[k] < 0 || (uint32_t)p.v[k] >= f->vertex_count) { herr.set(CRGPU_ERR_BAD_ARGUMENT, "vertex index out of range"); return; }
+					float v0[3], v1[3], v2[3], e1[3], e2[3];
+					f3(v0, f->vertices, (size_t)p.v[0]); f3(v1, f->vertices, (size_t)p.v[1]); f3(v2, f->vertices, (size_t)p.v[2]);
+					for (int k = 0; k < 3; ++k) { e1[k] = v0[k] - v1[k]; e2[k] = v2[k] - v0[k]; }
+					volatile float m0 = e1[1] * e2[2], m1 = e1[2] * e2[1], m2 = e1[2] * e2[0], m3 = e1[0] * e2[2], m4 = e1[0] * e2[1], m5 = e1[1] * e2[0];
+					sp.n0[0] = m0 - m1; sp.n0[1] = m2 - m3; sp.n0[2] = m4 - m5;
+				}
+				bool has_uv = mesh.texcoord_count != 0 && p.t[0] != -1;                          /* instance.c:151-153 */
+				if (has_uv) {
+					for (int k = 0; k < 3; ++k)
+						if (p.t[k] < 0 || (uint32_t)p.t[k] >= f->texcoord_count) { herr.set(CRGPU_ERR_BAD_ARGUMENT, "texcoord index out of range"); return; }
+					sp.t0[0] = f->texcoords[2 * (size_t)p.t[0]]; sp.t0[1] = f->texcoords[2 * (size_t)p.t[0] + 1];
+					sp.t1[0] = f->texcoords[2 * (size_t)p.t[1]]; sp.t1[1] = f->texcoords[2 * (size_t)p.t[1] + 1];
+					sp.t2[0] = f->texcoords[2 * (size_t)p.t[2]]; sp.t2[1] = f->texcoords[2 * (size_t)p.t[2] + 1];
+				}
+				if (p.material >= mesh.material_count) { herr.set(CRGPU_ERR_BAD_ARGUMENT, "poly material index out of range"); return; }
+				sp.material = mesh.material_offset + p.material;
+				sp.flags = (has_n ? 1u : 0u) | (has_uv ? 2u : 0u);
+				spolys[mesh.poly_offset + i] = sp;
+			}
+		});
+	}
+	pair_thread.join();
+	if (herr.code) { crgpu_scene_destroy(s); return fail(herr.code, "%s", herr.msg); }
 
 	/* instances */
 	std::vector<DevInstance> insts(f->instance_count);
