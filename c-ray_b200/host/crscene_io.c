@@ -10,6 +10,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <pthread.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 struct section { const void *ptr; size_t bytes; };
 
@@ -66,32 +71,69 @@ int crscene_save(const struct crs_scene *s, const char *path) {
 	return ok ? 0 : -2;
 }
 
+/* Files are mapped, not read: the arrays are only ever read (the uploader copies them to the GPU once), so a private
+ * read-only mapping of the page cache saves the 50 MB copy a frame-per-scene host pays (~25 ms for hdr.json).
+ * Live mappings are remembered so that crscene_free can tell them from malloc'ed scenes (the loader's, crloader.h). */
+#define CRS_MAX_MAPPINGS 256
+static struct { void *base; size_t size; } g_maps[CRS_MAX_MAPPINGS];
+static pthread_mutex_t g_maps_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static int remember_mapping(void *base, size_t size) {
+	int ok = 0;
+	pthread_mutex_lock(&g_maps_lock);
+	for (int i = 0; i < CRS_MAX_MAPPINGS && !ok; ++i)
+		if (!g_maps[i].base) { g_maps[i].base = base; g_maps[i].size = size; ok = 1; }
+	pthread_mutex_unlock(&g_maps_lock);
+	return ok;
+}
+
+static size_t forget_mapping(void *base) {
+	size_t size = 0;
+	pthread_mutex_lock(&g_maps_lock);
+	for (int i = 0; i < CRS_MAX_MAPPINGS && !size; ++i)
+		if (g_maps[i].base == base) { size = g_maps[i].size; g_maps[i].base = NULL; g_maps[i].size = 0; }
+	pthread_mutex_unlock(&g_maps_lock);
+	return size;
+}
+
 int crscene_load(struct crs_scene *out, const char *path) {
 	memset(out, 0, sizeof(*out));
-	FILE *f = fopen(path, "rb");
-	if (!f) return -1;
-	if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return -2; }
-	long size = ftell(f);
-	if (size < (long)header_bytes()) { fclose(f); return -3; }
-	rewind(f);
-	uint8_t *buf = NULL;
-	if (posix_memalign((void **)&buf, 64, (size_t)size) != 0) { fclose(f); return -4; }
-	if (fread(buf, 1, (size_t)size, f) != (size_t)size) { fclose(f); free(buf); return -2; }
-	fclose(f);
+	const int fd = open(path, O_RDONLY);
+	if (fd < 0) return -1;
+	struct stat st;
+	if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); return -2; }
+	const long size = (long)st.st_size;
+	if (size < (long)header_bytes()) { close(fd); return -3; }
+	uint8_t *buf = mmap(NULL, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
+	int mapped = buf != MAP_FAILED && remember_mapping(buf, (size_t)size);
+	if (!mapped) {                                            /* no mapping (or the table is full): read the file instead */
+		if (buf != MAP_FAILED) munmap(buf, (size_t)size);
+		buf = NULL;
+		if (posix_memalign((void **)&buf, 64, (size_t)size) != 0) { close(fd); return -4; }
+		size_t got = 0;
+		while (got < (size_t)size) {
+			const ssize_t n = read(fd, buf + got, (size_t)size - got);
+			if (n <= 0) { close(fd); free(buf); return -2; }
+			got += (size_t)n;
+		}
+	}
+	close(fd);
+#define CRS_FAIL(code) do { if (mapped) munmap(buf, forget_mapping(buf)); else free(buf); memset(out, 0, sizeof(*out)); return (code); } while (0)
 	uint32_t magic, version;
 	uint64_t total;
 	memcpy(&magic, buf, 4); memcpy(&version, buf + 4, 4); memcpy(&total, buf + 8, 8);
-	if (magic != CRS_MAGIC || version != CRS_VERSION || total != (uint64_t)size) { free(buf); return -5; }
+	if (magic != CRS_MAGIC || version != CRS_VERSION || total != (uint64_t)size) CRS_FAIL(-5);
 	memcpy(out, buf + 16, sizeof(*out));
 	struct section sec[14];
 	sections_of(out, sec); /* sizes only; pointers are NULL in the file */
 	size_t off = header_bytes();
 	void *ptrs[14];
 	for (int i = 0; i < 14; ++i) {
-		if (off > (size_t)size || sec[i].bytes > (size_t)size - off) {   /* overflow-safe: counts come from the file */ free(buf); memset(out, 0, sizeof(*out)); return -6; }
+		if (off > (size_t)size || sec[i].bytes > (size_t)size - off) CRS_FAIL(-6);      /* overflow-safe: counts come from the file */
 		ptrs[i] = sec[i].bytes ? buf + off : NULL;
 		off += align16(sec[i].bytes);
 	}
+#undef CRS_FAIL
 	out->instances = ptrs[0]; out->spheres = ptrs[1]; out->meshes = ptrs[2]; out->materials = ptrs[3];
 	out->nodes = ptrs[4]; out->textures = ptrs[5]; out->bvhs = ptrs[6]; out->bvh_nodes = ptrs[7];
 	out->prim_indices = ptrs[8]; out->polys = ptrs[9]; out->vertices = ptrs[10]; out->normals = ptrs[11];
@@ -101,7 +143,10 @@ int crscene_load(struct crs_scene *out, const char *path) {
 }
 
 void crscene_free(struct crs_scene *s) {
-	if (s && s->owner) free(s->owner);
+	if (s && s->owner) {
+		const size_t mapped = forget_mapping(s->owner);
+		if (mapped) munmap(s->owner, mapped); else free(s->owner);
+	}
 	if (s) memset(s, 0, sizeof(*s));
 }
 
