@@ -269,7 +269,17 @@ static inline bool node_test(const struct crs_bvh_node *node, v3 invDir, v3 scal
 	return tMin <= tMax;
 }
 
-struct trav_ctx { const struct crs_scene *s; struct cro_counters *ctr; };
+/* optional event trace of the traversal, at the granularity of the GPU kernel's state machine (crgpu_trace.cuh): used by
+ * tools/k2_warp_model.py to study warp scheduling policies offline.  Event bytes: 0 = top-level child-pair step,
+ * 1 = mesh instance step, 2 = sphere instance step, 64+k = bottom-level child-pair step that tested k triangles (k <= 63). */
+struct cro_trace { uint8_t *buf; size_t cap, len; size_t pair_at; uint16_t x, y, pass; };
+struct trav_ctx { const struct crs_scene *s; struct cro_counters *ctr; struct cro_trace *tr; };
+static inline void tr_event(const struct trav_ctx *c, uint8_t code) {
+	if (c->tr && c->tr->len < c->tr->cap) { c->tr->pair_at = c->tr->len; c->tr->buf[c->tr->len++] = code; }
+}
+static inline void tr_tri(const struct trav_ctx *c, size_t at) {
+	if (c->tr && at < c->tr->cap && c->tr->buf[at] < 127) c->tr->buf[at]++;
+}
 
 static bool leaf_bottom(const struct trav_ctx *c, const struct crs_mesh *mesh, const struct crs_bvh *bvh,
 						const struct crs_bvh_node *leaf, const struct ray *ray, struct hit *isect) { /* bvh.c:443-462 */
@@ -279,6 +289,7 @@ static bool leaf_bottom(const struct trav_ctx *c, const struct crs_mesh *mesh, c
 		int local = c->s->prim_indices[bvh->prim_offset + leaf->first_child_or_prim + (uint32_t)i];
 		int polyIdx = (int)mesh->poly_offset + local;
 		if (c->ctr) c->ctr->tri_tests++;
+		if (c->tr) tr_tri(c, c->tr->pair_at);
 		if (ray_triangle(c->s, ray, polyIdx, isect)) {
 			isect->poly = polyIdx;
 			found = true;
@@ -306,6 +317,7 @@ static bool intersect_sphere_inst(const struct trav_ctx *c, const struct crs_ins
 	struct ray copy = { xf_point(inst->Ainv, ray->o), xf_vector(inst->Ainv, ray->d) };
 	copy.o = v3add(copy.o, v3scale(copy.d, sp->ray_offset));
 	if (c->ctr) c->ctr->sphere_tests++;
+	tr_event(c, 2);
 	if (ray_sphere(&copy, sp->radius, isect)) {
 		isect->uv = texmap_sphere(isect->n);
 		isect->poly = -1;
@@ -337,6 +349,7 @@ static bool intersect_mesh_inst(const struct trav_ctx *c, const struct crs_insta
 	struct ray copy = { xf_point(inst->Ainv, ray->o), xf_vector(inst->Ainv, ray->d) };
 	copy.o = v3add(copy.o, v3scale(copy.d, mesh->ray_offset));
 	if (c->ctr) c->ctr->inst_visits++;
+	tr_event(c, 1);
 	if (traverse(c, mesh->bvh, (int)inst->object, &copy, isect)) {
 		isect->uv = texmap_mesh(c->s, mesh, isect);
 		isect->material = (int)(mesh->material_offset + c->s->polys[isect->poly].material);
@@ -385,6 +398,7 @@ static bool traverse(const struct trav_ctx *c, uint32_t bvhIdx, int meshIdx, con
 
 	if (bvh->node_count == 1) {                                                             /* bvh.c:382-387 */
 		float tEntry;
+		if (mesh) tr_event(c, 64);                               /* single-leaf BVH: one step that tests the leaf's triangles */
 		if (node_test(nodes, invDir, scaledStart, oct, maxDist, &tEntry)) return LEAF(nodes);
 		return false;
 	}
@@ -395,6 +409,7 @@ static bool traverse(const struct trav_ctx *c, uint32_t bvhIdx, int meshIdx, con
 		const struct crs_bvh_node *left = &nodes[firstChild];
 		const struct crs_bvh_node *right = &nodes[firstChild + 1];
 		if (c->ctr) c->ctr->node_pairs++;
+		tr_event(c, mesh ? 64 : 0);
 		float tL, tR;
 		bool hitL = node_test(left, invDir, scaledStart, oct, maxDist, &tL);
 		bool hitR = node_test(right, invDir, scaledStart, oct, maxDist, &tR);
@@ -665,7 +680,20 @@ static col path_trace(const struct trav_ctx *c, struct ray ray, int maxDepth, st
 	col weight = { 1, 1, 1, 1 };
 	col final = { 0, 0, 0, 1 };
 	for (int depth = 0; depth < maxDepth; ++depth) {
+		size_t hdr = 0;
+		const size_t HDR = 36;
+		int have_hdr = 0;
+		if (c->tr && c->tr->len + HDR <= c->tr->cap) {           /* record header: x, y, pass, depth (u16), event count (u32), o, d (6 x f32) */
+			hdr = c->tr->len;
+			have_hdr = 1;
+			const uint16_t h[4] = { c->tr->x, c->tr->y, c->tr->pass, (uint16_t)depth };
+			const float od[6] = { ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z };
+			memcpy(c->tr->buf + hdr, h, 8);
+			memcpy(c->tr->buf + hdr + 12, od, 24);
+			c->tr->len += HDR;
+		}
 		struct hit isect = closest_isect(c, &ray);
+		if (have_hdr) { const uint32_t n = (uint32_t)(c->tr->len - hdr - HDR); memcpy(c->tr->buf + hdr + 8, &n, 4); }
 		if (c->ctr && (uint64_t)(depth + 1) > c->ctr->max_depth) c->ctr->max_depth = (uint64_t)(depth + 1);
 		if (isect.inst < 0) {
 			final = cadd(final, cmul(weight, sample_bsdf(s, s->background, r, &isect).color));
@@ -698,7 +726,7 @@ struct job {
 static void *render_rows(void *arg) {
 	struct job *j = arg;
 	const struct crs_scene *s = j->s;
-	struct trav_ctx c = { s, j->count ? &j->ctr : NULL };
+	struct trav_ctx c = { s, j->count ? &j->ctr : NULL, NULL };
 	const int W = (int)s->prefs.image_width, H = (int)s->prefs.image_height;
 	const int maxPasses = (int)s->prefs.sample_count, bounces = (int)s->prefs.bounces;
 	for (int y = j->yend - 1; y > j->ybegin - 1; --y) {
@@ -730,6 +758,26 @@ static void *run_chunks(void *arg) {
 	struct runner *r = arg;
 	for (int i = r->first; i < r->n; i += r->step) render_rows(&r->jobs[i]);
 	return NULL;
+}
+
+/* Traversal event trace of every ray of a region (single thread; pixels row-major y up, passes innermost), see struct cro_trace.
+ * Returns the number of bytes written (records are dropped, not truncated, once the buffer is full). */
+size_t cro_trace_region(const struct crs_scene *s, int x0, int y0, int x1, int y1, int pass_begin, int pass_count, uint8_t *buf, size_t cap) {
+	struct cro_trace tr = { buf, cap, 0, 0, 0, 0, 0 };
+	struct trav_ctx c = { s, NULL, &tr };
+	const int W = (int)s->prefs.image_width;
+	const int maxPasses = (int)s->prefs.sample_count, bounces = (int)s->prefs.bounces;
+	for (int y = y0; y < y1; ++y)
+		for (int x = x0; x < x1; ++x)
+			for (int pass = pass_begin; pass < pass_begin + pass_count; ++pass) {
+				struct rng r = { 0, NULL };
+				rng_init(&r, (uint32_t)(y * W + x), pass, maxPasses);
+				tr.x = (uint16_t)x; tr.y = (uint16_t)y; tr.pass = (uint16_t)pass;
+				struct ray ray = camera_ray(&s->camera, x, y, &r);
+				if (tr.len + 4096 > tr.cap) return tr.len;
+				path_trace(&c, ray, bounces, &r);
+			}
+	return tr.len;
 }
 
 int cro_render(const struct crs_scene *s, int x0, int y0, int x1, int y1, int pass_begin, int pass_count,
@@ -781,7 +829,7 @@ void cro_sampler_kat(uint32_t pixIdx, int pass, int maxPasses, int n, float *out
 void cro_trace_kat(const struct crs_scene *s, int x, int y, int pass, struct cro_hit_kat *k) {
 	memset(k, 0, sizeof *k);
 	const int W = (int)s->prefs.image_width;
-	struct trav_ctx c = { s, NULL };
+	struct trav_ctx c = { s, NULL, NULL };
 	k->x = x; k->y = y; k->pixIdx = y * W + x;
 	struct rng r = { 0, NULL };
 	rng_init(&r, (uint32_t)k->pixIdx, pass, (int)s->prefs.sample_count);
