@@ -150,6 +150,26 @@ def simulate(rays, policy="phase", burst=3, refill=16, persistent=True, cooperat
                     for r in insts:
                         r.take()
                     m.add(W_INST, len(insts))
+            elif policy == "leafwait":
+                # node rounds in which a lane that reaches a leaf WAITS (its triangles untested) until no lane can advance or
+                # `burst` rounds passed; then ONE triangle phase for all waiting lanes; then the instance steps.  Visiting order
+                # and the distance used for culling are unchanged for every ray: only the warp's interleaving differs.
+                waiting = {}
+                for _ in range(burst):
+                    nodes = [r for r in live if id(r) not in waiting and r.wants_node()]
+                    if not nodes:
+                        break
+                    m.add(W_NODE, len(nodes))
+                    for r in nodes:
+                        c = r.take()
+                        if c > 64:
+                            waiting[id(r)] = c - 64
+                tri_rounds(m, list(waiting.values()), cooperative)
+                insts = [r for r in live if r.wants_inst()]
+                if insts:
+                    for r in insts:
+                        r.take()
+                    m.add(W_INST, len(insts))
             else:
                 # phase-separated: up to `burst` node rounds, then the pending instance steps together
                 for _ in range(burst):
@@ -205,6 +225,10 @@ def main():
             ("  refill<24", dict(policy="phase", burst=3, refill=24)),
             ("  refill<31 (refill whenever a lane is free)", dict(policy="phase", burst=3, refill=31)),
             ("  + cooperative triangle tests", dict(policy="phase", burst=3, refill=16, cooperative=True)),
+            ("leaves wait for a common triangle phase, burst 4", dict(policy="leafwait", burst=4, refill=16)),
+            ("leaves wait, burst 8", dict(policy="leafwait", burst=8, refill=16)),
+            ("leaves wait, burst 8, refill<24", dict(policy="leafwait", burst=8, refill=24)),
+            ("leaves wait, burst 8 + cooperative triangles", dict(policy="leafwait", burst=8, refill=16, cooperative=True)),
             ("  refill<31 + cooperative triangles", dict(policy="phase", burst=3, refill=31, cooperative=True)),
         ]
         for name, kw in rows:
