@@ -40,18 +40,43 @@ def unpack_into(fb, rects, flat):
         off += n
 
 
+_index_cache = {}
+
+
+def _pixel_indices(W, H, tile, world, device):
+    """Per rank: the flat pixel indices (into fb.view(-1, 3)) of its tiles in pack() order, built once per geometry."""
+    key = (W, H, tile, world, str(device))
+    hit = _index_cache.get(key)
+    if hit is None:
+        cols = torch.arange(W, dtype=torch.int64)
+        per_rank = []
+        for r in range(world):
+            parts = []
+            for (x0, y0, x1, y1) in rank_rects(W, H, tile, r, world):
+                rows = torch.arange(H - y1, H - y0, dtype=torch.int64)          # storage rows of the tile, top first
+                parts.append((rows[:, None] * W + cols[None, x0:x1]).reshape(-1))
+            per_rank.append((torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64)).to(device))
+        hit = _index_cache[key] = per_rank
+    return hit
+
+
 def gather_to_rank0(fb, W, H, tile, rank, world, dist):
-    """One gather of every rank's packed tiles to rank 0 (equal-size padded messages)."""
+    """One gather of every rank's packed tiles to rank 0 (equal-size padded messages).  Packing and unpacking are one
+    index_select / index_copy_ each (the tile grid of a 1080p frame is 510 tiles: copying them one by one costs hundreds
+    of small launches on rank 0)."""
     if world == 1:
         return
-    all_rects = [rank_rects(W, H, tile, r, world) for r in range(world)]
-    sizes = [sum((x1 - x0) * (y1 - y0) * 3 for (x0, y0, x1, y1) in rs) for rs in all_rects]
-    pad = max(sizes)
+    idx = _pixel_indices(W, H, tile, world, fb.device)
+    pad = max(int(i.numel()) for i in idx) * 3
+    px = fb.view(-1, 3)
     buf = torch.zeros(pad, device=fb.device, dtype=torch.float32)
-    mine = pack(fb, all_rects[rank])
-    buf[:mine.numel()] = mine
+    mine = idx[rank]
+    if mine.numel():
+        buf[:mine.numel() * 3] = px.index_select(0, mine).reshape(-1)
     outs = [torch.empty(pad, device=fb.device, dtype=torch.float32) for _ in range(world)] if rank == 0 else None
     dist.gather(buf, outs, dst=0)
     if rank == 0:
         for r in range(1, world):
-            unpack_into(fb, all_rects[r], outs[r])
+            n = int(idx[r].numel())
+            if n:
+                px.index_copy_(0, idx[r], outs[r][:n * 3].view(n, 3))

@@ -70,3 +70,22 @@ def test_shard_helpers():
     for r in rects[::2]:
         assert torch.equal(shard.rect_view(fb2, r), shard.rect_view(fb, r))
     assert shard.rect_view(fb, (0, 0, 16, 16)).shape == (16, 16, 3) and shard.rect_view(fb, (48, 32, 50, 35)).shape == (3, 2, 3)
+
+
+def test_gather_index_path_equals_tile_by_tile_copies():
+    """gather_to_rank0 packs/unpacks with one index_select / index_copy_ per rank; same bytes as copying tile by tile."""
+    import torch
+    import shard
+    W, H, t, world = 200, 117, 32, 3
+    fb = torch.arange(H * W * 3, dtype=torch.float32).view(H, W, 3)
+    idx = shard._pixel_indices(W, H, t, world, fb.device)
+    assert sum(int(i.numel()) for i in idx) == W * H
+    for r in range(world):
+        rects = shard.rank_rects(W, H, t, r, world)
+        a = shard.pack(fb, rects)
+        b = fb.view(-1, 3).index_select(0, idx[r]).reshape(-1)
+        assert torch.equal(a, b)
+        x, y = torch.zeros_like(fb), torch.zeros_like(fb)
+        shard.unpack_into(x, rects, a)
+        y.view(-1, 3).index_copy_(0, idx[r], b.view(-1, 3))
+        assert torch.equal(x, y)
