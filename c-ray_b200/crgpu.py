@@ -109,7 +109,7 @@ def device_count():
 class GpuScene:
     """A scene resident on one GPU (crgpu_scene) plus its device framebuffer."""
 
-    def __init__(self, crscene_path, width=0, height=0, samples=0, bounces=0, device=0, max_paths=None):
+    def __init__(self, crscene_path, width=0, height=0, samples=0, bounces=0, device=0, max_paths=None, force_bounces=None):
         L = lib()
         if str(crscene_path).lower().endswith(".json"):
             # a c-ray JSON scene: parsed + BVH-built on the host by libcrloader.so (include/crloader.h)
@@ -120,7 +120,9 @@ class GpuScene:
             rc = L.crscene_load(C.byref(self.flat), os.fsencode(crscene_path))
             if rc != 0:
                 raise CrgpuError(f"crscene_load({crscene_path}) failed: {rc}")
-        L.crscene_set_config(C.byref(self.flat), width, height, samples, bounces)
+        L.crscene_set_config(C.byref(self.flat), width, height, samples, bounces)     # 0 = keep the scene's value
+        if force_bounces is not None:
+            self.flat.prefs.bounces = force_bounces                                       # (so that 0 itself can be requested)
         self.W, self.H = self.flat.prefs.image_width, self.flat.prefs.image_height
         self.samples, self.bounces = self.flat.prefs.sample_count, self.flat.prefs.bounces
         self.handle = C.c_void_p()

@@ -644,6 +644,9 @@ static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, in
 		td.pass_begin = pb;
 		td.pass_count = (pass_begin + pass_count - pb) < (int)batch ? (pass_begin + pass_count - pb) : (int)batch;
 		crg_launch_generate(s->dev, s->wb, td, grid, st); ++launches;
+		/* bounces == 0: pathTrace's loop never runs and every sample is black (pathtrace.c:34-36,59).  L is write-once by
+		 * design (cr_add_radiance / cr_finish_path), so with no bounce nothing would write it: clear it here instead */
+		if (maxDepth == 0) CU(cudaMemsetAsync(s->wb.L, 0, (size_t)tile_pixels * (size_t)td.pass_count * sizeof(float4), st));
 		int cur = 0;
 		for (int depth = 0; depth < maxDepth; ++depth) {
 			if (depth >= CRG_TAIL_FROM && !count) { crg_launch_tail(s->dev_copy, s->wb, cur, depth, maxDepth, st); ++launches; }

@@ -288,8 +288,10 @@ CRD BsdfSample cr_sample_leaf(const DevScene &sc, const crs_node &n, uint64_t &r
 		return s;
 	}
 	case CRS_BSDF_GLASS: {                                                                  /* glass.c:41-87 */
-		v3 refracted = v3make(0.0f, 0.0f, 0.0f);
+		/* glass.c:47 reads an uninitialised `refracted` when refract() failed and the draw is exactly 1.0f; defined as
+		 * "total internal reflection always reflects" (DESIGN.md deviation #3, same as oracle/cray_oracle.c) */
 		v3 reflected = v3reflect(rec.inc_d, rec.n);
+		v3 refracted = reflected;
 		const float IOR = Nodes::value(sc, n.in[2], rec);
 		const float prob = cr_fresnel_probability(rec, IOR, refracted);
 		const float rough = Nodes::value(sc, n.in[1], rec);

@@ -583,8 +583,13 @@ static struct bsdf_sample sample_bsdf(const struct crs_scene *s, int node, struc
 		return (struct bsdf_sample){ reflected, eval_color(s, n->in[0], rec) };
 	}
 	case CRS_BSDF_GLASS: {                                                            /* glass.c:41-87 */
-		v3 outward, refracted = { 0, 0, 0 };
+		/* glass.c:47 declares `refracted` uninitialised and reads it (:76-80) when refract() failed (total internal reflection)
+		 * and the draw is exactly 1.0f (129 of 2^32 draws): the compiled reference then scatters along (0, 0, <stale stack word>),
+		 * which is not a function of the path.  DEFINED here (DESIGN.md deviation #3, identical in crgpu_shade.cuh): total
+		 * internal reflection always reflects, i.e. `refracted` starts out as `reflected`. */
+		v3 outward;
 		v3 reflected = v3reflect(rec->incident.d, rec->n);
+		v3 refracted = reflected;
 		float niOverNt, prob, cosine;
 		float IOR = eval_value(s, n->in[2], rec);
 		if (v3dot(rec->incident.d, rec->n) > 0.0f) {

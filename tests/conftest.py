@@ -11,10 +11,16 @@ for p in (ROOT, os.path.join(ROOT, "c-ray_b200"), os.path.join(ROOT, "tests")):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 BUILT = os.path.join(ROOT, "scenes", "_built")
 GOLDEN_SCENES = ["g_nodes", "g_legacy", "g_single", "g_meshmat"]
+SUMMARY_LINES = []   # headline parity figures (tests/test_zz_full_config.py): repeated in the terminal summary so the run's tail shows them
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_terminal_summary(terminalreporter):
+    for line in SUMMARY_LINES:
+        terminalreporter.write_line(line)
 
 
 @pytest.fixture(scope="session", autouse=True)
