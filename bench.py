@@ -2,14 +2,17 @@
 """bench.py — Mray/s (and Msample/s) of the B200 path-trace hot loop on BASELINE.json's headline config.
 
 A "step" is one complete render of the workload frame: default = configs[1] of BASELINE.json,
-input/hdr.json at 1920x1080, 1000 spp, 32 bounces (scene flattened by the reference's own loader at build
-time: scenes/_built/hdr.crscene).  Image tiles (the reference's quantizeImage grid) are sharded
-round-robin over the ranks; the frame is fixed, so this is STRONG scaling.  With N>1 the fp32
-framebuffer tiles are gathered on rank 0 over NCCL inside the timed region.
+input/hdr.json at 1920x1080, 1000 spp, 32 bounces; --workload refraction | venus | hdr8k are configs[2..4].
+The tile queue of the host C dispatcher (quantizeImage order) is dealt out to the ranks by queue position
+(k % world, cr_renderer.c takeRankTiles); the frame is fixed, so this is STRONG scaling.  With N>1 the fp32
+framebuffer tiles are gathered on rank 0 over NCCL (libcrgpu_nccl.so) inside the timed region.
 
-  value      Mray/s, whole job, scene + framebuffer resident in HBM, device-timed (CUDA events), max over ranks
-  e2e        same metric through the public C ABI with HOST buffers: crgpu_scene_create from the host-resident
-             flat scene (H2D of every array) + render + NCCL gather + crgpu_framebuffer_read (D2H), wall clock
+  value      Mray/s, whole job, scene + framebuffer resident in HBM, device-timed (CUDA events), max over ranks;
+             the tile gather of N>1 is the product's (libcrgpu_nccl.so, grouped ncclSend/ncclRecv) on the same stream
+  e2e        same metric through the reference-facing C API with HOST buffers: libcrhost.so `renderFrame` (the host C
+             mirror of c-ray's tile dispatcher) — H2D of the prepared scene from pinned host memory, tiles, NCCL gather
+             in C, D2H of the fp32 renderBuffer + the 8-bit image — wall clock around the call, max over ranks.
+             The scene is loaded from input/*.json by THIS repository's loader (libcrloader.so), once, like loadScene.
   roofline   K2 (k_trace) algorithmic bytes / its CUDA-event time, vs the measured HBM copy peak
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/cray_ref_stock, pthreads, all host cores) on a bounded
              sample (same frame, fewer spp) — a reported baseline, not the optimisation target
@@ -29,11 +32,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "c-ray_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-WORKLOADS = {   # BASELINE.json configs[1..3]
-    "hdr": dict(scene="hdr", width=1920, height=1080, spp=1000, bounces=32),
-    "refraction": dict(scene="refraction", width=1920, height=1080, spp=2500, bounces=512),
-    "venus": dict(scene="venus", width=2560, height=1600, spp=1000, bounces=25),
-    "scene": dict(scene="scene", width=320, height=200, spp=16, bounces=4),
+WORKLOADS = {   # BASELINE.json configs[0..4]
+    "hdr": dict(scene="hdr", width=1920, height=1080, spp=1000, bounces=32),             # C2: the configuration the metric is quoted on (default)
+    "refraction": dict(scene="refraction", width=1920, height=1080, spp=2500, bounces=512),   # C3
+    "venus": dict(scene="venus", width=2560, height=1600, spp=1000, bounces=25),         # C4
+    "hdr8k": dict(scene="hdr", width=7680, height=4320, spp=4000, bounces=32),           # C5: the 8-GPU frame (fits one GPU too; --spp reduces it)
+    "scene": dict(scene="scene", width=320, height=200, spp=16, bounces=4),              # C1 geometry
 }
 PEAK_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -49,10 +53,12 @@ def parse_args():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--bounces", type=int, default=0)
-    ap.add_argument("--tile", type=int, default=-1, help="tile edge of the tile grid (default 64, the scene's own tile size; 0 = one whole-frame rectangle)")
+    ap.add_argument("--tile", type=int, default=0, help="tile edge of the dispatcher's tile grid (default 64)")
     ap.add_argument("--max-paths", type=int, default=0, help="paths in flight per wavefront batch (0 = library default)")
     ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the informational loader-vs-reference-loader timing")
+    ap.add_argument("--crscene", action="store_true", help="take the scene from scenes/_built/*.crscene (reference loader's export) instead of parsing the JSON")
     return ap.parse_args()
 
 
@@ -169,7 +175,7 @@ def reference_arm(args, w, rank):
     """bench.py --impl reference: the reference's own CPU implementation of the path, rank 0 only."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_threads()
     spp = args.cpu_spp or max(1, min(w["spp"], int(5.0e7 / (w["width"] * w["height"])) or 1))   # a few seconds of CPU rendering per step
     rays_per_sample = float(os.environ.get("CRAY_RAYS_PER_SAMPLE", "0")) or None
     times = []
@@ -190,10 +196,10 @@ def reference_arm(args, w, rank):
     line = {"metric": "Mray/s", "value": round(value, 3), "unit": "Mray/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * total_s / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "bundled scene input/%s.json (reference assets copied at build time)" % w["scene"], "impl": "reference",
-            "config": {"workload": f"input/{w['scene']}.json {w['width']}x{w['height']} {w['spp']} spp {w['bounces']} bounces", "spp_per_step": spp,
+            "config": {"workload": f"input/{w['scene']}.json {w['width']}x{w['height']} {w['spp']} spp {w['bounces']} bounces", "name": args.workload, "spp_per_step": spp,
                        "note": "bounded sample: same frame, fewer spp (CPU cost is linear in spp, renderer.c:275)"},
             "msample_per_s": round(msample, 3), "rays_per_sample": round(rps, 4),
-            "cpu_baseline": {"value": round(value, 3), "unit": "Mray/s", "cores": threads, "kind": "reference",
+            "cpu_baseline": {"value": round(value, 3), "unit": "Mray/s", "cores": threads, "kind": "reference", "host": host_cpus(),
                              "sample": f"{w['width']}x{w['height']} x {spp} spp per step, pthreads -j {threads}, stock flags (-O2 -ftree-vectorize -march=x86-64-v3)"},
             "e2e": {"value": round(value, 3), "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -210,6 +216,37 @@ def oracle_rays_per_sample(w, spp):
     return c["rays"] / c["paths"]
 
 
+def host_cpus():
+    """What this process may actually use: os.cpu_count() is the machine, not the cgroup/affinity share (a 5x swing of the CPU
+    arm between two boxes that both 'have 128 cores' was exactly that)."""
+    out = {"cpu_count": os.cpu_count() or 1}
+    try:
+        out["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:   # noqa: BLE001
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            out["cgroup_" + os.path.basename(path)] = open(path).read().strip()
+            break
+        except OSError:
+            continue
+    try:
+        out["loadavg_1m"] = round(os.getloadavg()[0], 1)
+    except OSError:
+        pass
+    return out
+
+
+def usable_threads():
+    h = host_cpus()
+    n = h.get("affinity", h["cpu_count"])
+    q = h.get("cgroup_cpu.max", "")
+    m = re.match(r"(\d+)\s+(\d+)", q)
+    if m and int(m.group(2)) > 0:
+        n = max(1, min(n, int(int(m.group(1)) / int(m.group(2)) + 0.5)))
+    return n
+
+
 def main():
     args = parse_args()
     w = workload(args)
@@ -220,10 +257,11 @@ def main():
         reference_arm(args, w, rank)
         return
 
+    import zlib
     import numpy as np
     import torch
     import crgpu
-    import shard
+    import crhost
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
@@ -236,35 +274,57 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    work_stream = torch.cuda.Stream(device=dev)      # library kernels, NCCL gather and the timing events all live on this stream
+    work_stream = torch.cuda.Stream(device=dev)      # library kernels, the C NCCL gather and the timing events all live on this stream
     torch.cuda.set_stream(work_stream)
 
     W, H, spp, bounces = w["width"], w["height"], w["spp"], w["bounces"]
-    scene_path = os.path.join(ROOT, "scenes", "_built", w["scene"] + ".crscene")
-    if not os.path.exists(scene_path):
-        raise SystemExit(f"{scene_path} missing: run __graft_entry__.build() in the build container")
-    tile = args.tile if args.tile >= 0 else 64      # tile-ordered pixel lists keep warps on compact 2D footprints (faster than row-major)
-    g = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
-    rects = shard.rank_rects(W, H, tile, rank, world) if tile else [(0, 0, W, H)]
+    tile = args.tile if args.tile > 0 else 64       # the tile dispatcher's grid (tile-ordered pixel lists keep warps on compact 2D footprints)
 
-    # zero-copy torch view of the device framebuffer (for the NCCL gather)
-    ptr, nbytes = g.device_ptr()
+    # ---- the scene: input/<scene>.json through THIS repository's loader, like loadScene: once, outside the frames
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    js = os.path.join("input", w["scene"] + ".json")
+    flat_fallback = os.path.join(ROOT, "scenes", "_built", w["scene"] + ".crscene")
+    t_in = time.perf_counter()
+    if os.path.exists(os.path.join(refdir, js)) and not args.crscene:
+        cwd = os.getcwd()
+        os.chdir(refdir)                   # node-graph texture paths are relative to the reference's working directory (sceneloader.c:783)
+        try:
+            R = crhost.Renderer(js, W, H, spp, bounces, gpus=1, tile=tile, quiet=True)
+        finally:
+            os.chdir(cwd)
+        scene_src = f"input/{w['scene']}.json parsed + BVH-built by libcrloader.so (this repository's loader)"
+    elif os.path.exists(flat_fallback):
+        R = crhost.Renderer(flat_fallback, W, H, spp, bounces, gpus=1, tile=tile, quiet=True)
+        scene_src = f"scenes/_built/{w['scene']}.crscene (flattened by the reference loader at build time)"
+    else:
+        raise SystemExit("no scene: neither oracle/_ref/input nor scenes/_built present — run __graft_entry__.build() in the build container")
+    ingest_s = time.perf_counter() - t_in
 
-    class _Fb:
-        __cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f4", "data": (ptr, False), "version": 2}
-    fb = torch.as_tensor(_Fb(), device=dev)
+    # ---- the GPU group: rank 0 makes the NCCL id, torch.distributed (the launcher's plumbing) hands it out, the C host joins
+    if world > 1:
+        box = [crhost.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        R.join(box[0], rank, world, local)
+    else:
+        R.join(None, 0, 1, local)
+    t_p = time.perf_counter()
+    R.prepare()                                   # re-layout for the kernels into pinned host memory (part of scene loading)
+    prepare_s = time.perf_counter() - t_p
+    my_rects, owner, all_rects = R.rank_tiles(rank, world)
 
-    def gather_to_rank0():
-        shard.gather_to_rank0(fb, W, H, tile, rank, world, dist)
+    # ---- value: scene + framebuffer resident, device-timed ------------------------------------------------------------------
+    g = crgpu.GpuScene(None, samples=spp, bounces=bounces, device=local, max_paths=args.max_paths or None, prepared=R.prepared())
+    gather = None
+    if world > 1:
+        gather = crgpu.RankGather(R.comm())
+        gather.set_stream(torch.cuda.current_stream(dev).cuda_stream)
 
     def step(flags=0):
-        """one complete frame: enqueue everything on torch's current stream, no host sync inside"""
+        """one complete frame: everything enqueued on torch's current stream"""
         g.clear()
-        if len(rects) == 1:
-            g.render_tile(*rects[0], flags=flags | crgpu.FLAG_ASYNC)
-        else:
-            g.render_tiles(rects, flags=flags | crgpu.FLAG_ASYNC)     # the rank's whole share of the tile grid as one wavefront
-        gather_to_rank0()
+        g.render_tiles(my_rects, flags=flags | crgpu.FLAG_ASYNC)       # the rank's whole share of the tile grid as one wavefront
+        if gather:
+            gather.gather(g, all_rects, owner, 0)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -280,16 +340,10 @@ def main():
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the library enqueues on torch's current stream (crgpu_set_stream), so these events bracket exactly its kernels
-    step_evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] if os.environ.get("CRAY_BENCH_STEP_TIMES") else None
     wall0 = time.perf_counter()
     ev0.record()
     for i in range(args.steps):
-        if step_evs:
-            step_evs[i].record()
         step()
-    if step_evs:
-        step_evs[-1].record()
     ev1.record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
@@ -297,10 +351,9 @@ def main():
     if ms < 0.9 * wall_ms:      # events that do not bracket the kernels (wrong stream) must never flatter the number
         sys.stderr.write(f"bench.py: CUDA-event time {ms:.1f} ms << wall {wall_ms:.1f} ms; reporting wall clock\n")
         ms = wall_ms
-    if step_evs and rank == 0:
-        sys.stderr.write("per-step ms: %s\n" % [round(step_evs[i].elapsed_time(step_evs[i + 1]), 1) for i in range(args.steps)])
     stats = g.get_stats()
     clocks = sampler.summary()
+    value_crc = zlib.crc32(g.read().tobytes()) if rank == 0 else 0
     tms = torch.tensor([ms, float(stats["rays"]), float(stats["paths"]), float(stats["kernel_launches"])], device=dev, dtype=torch.float64)
     if dist:
         mx = tms.clone()
@@ -313,49 +366,21 @@ def main():
     value = rays / ms / 1e3                      # Mray/s, whole job
     msample = paths / ms / 1e3
 
-    # ---- e2e through the C ABI with host buffers (scene upload + render + gather + read back) ---------------
-    g.close()
-    host_fb = np.empty((H, W, 3), dtype=np.float32)
-    h2d = os.path.getsize(scene_path)
-    barrier()
-    t0 = time.perf_counter()
-    e_rays = 0
-    e_steps = max(1, min(args.steps, 2))
-    for it in range(e_steps):
-        g2 = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
-        ptr = g2.device_ptr()[0]
-
-        class _Fb2:
-            __cuda_array_interface__ = {"shape": (H, W, 3), "typestr": "<f4", "data": (ptr, False), "version": 2}
-        fb = torch.as_tensor(_Fb2(), device=dev)
-        g = g2
-        g.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-        step()
-        e_rays += g.get_stats()["rays"]
-        if rank == 0:
-            g2.read(host_fb)
-        if it != e_steps - 1:
-            g2.close()
-    barrier()
-    e_ms = 1e3 * (time.perf_counter() - t0)
-    et = torch.tensor([e_ms, float(e_rays)], device=dev, dtype=torch.float64)
-    if dist:
-        a = et.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        b = et.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        e_ms, e_rays = float(a[0]), float(b[1])
-    e2e_value = e_rays / e_ms / 1e3
-
-    # ---- roofline of K2: one profiled step (per-kernel CUDA events) + one counted step (P/T/S/I) ---------------
-    step(flags=crgpu.FLAG_TIME_KERNELS)
-    prof = g.get_stats()
+    # ---- roofline of K2 / K3: one profiled step (per-kernel CUDA events) + one counted step (P/T/S/I) ---------------
+    if gather:
+        gather.use_own_stream()
+    g.use_own_stream()
+    g.clear()
+    prof = g.render_tiles(my_rects, flags=crgpu.FLAG_TIME_KERNELS)
     cspp = min(spp, 8)
-    gc = crgpu.GpuScene(scene_path, W, H, spp, bounces, device=local, max_paths=args.max_paths or None)
-    cnt = gc.render_tiles(rects, pass_begin=0, pass_count=cspp, flags=crgpu.FLAG_COUNT)
-    gc.close()
+    g.clear()
+    cnt = g.render_tiles(my_rects, pass_begin=0, pass_count=cspp, flags=crgpu.FLAG_COUNT)
+    g.close()
     P, T, S, I = (cnt[k] / cnt["rays"] for k in ("node_pairs", "tri_tests", "sphere_tests", "inst_visits"))
     b_ray = 64 * P + 80 * T + 128 * I + 16 * S + 72
     peak, peak_kind = peaks()
     trace_s = prof["trace_ms"] / 1e3
+    shade_s = prof["shade_ms"] / 1e3
     achieved = (prof["rays"] * b_ray / trace_s / 1e9) if trace_s > 0 else None
     traffic, traffic_note = None, None
     try:   # DRAM bytes of one K2 launch from the committed ncu --set full capture (not live: ncu replays kernels ~40x)
@@ -363,11 +388,11 @@ def main():
         mfile = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_metrics.json")))[-1]
         m = json.load(open(mfile))["kernels"]["k_trace"][0]
         traffic = int((m["dram_read"] + m["dram_write"]) * 1e9)
-        traffic_note = (f"{os.path.basename(mfile)}: k_trace bounce-1 launch of a 66M-path batch on input/hdr.json (~40M rays, {m['duration']:.2f} ms): "
-                        f"{traffic / 1e9:.2f} GB of DRAM traffic = ~80 B/ray (the 52-B ray/hit records + misses), far BELOW the 769 B/ray algorithmic "
-                        "figure because nodes and triangles are served by L1/L2")
+        traffic_note = (f"{os.path.basename(mfile)}: k_trace bounce-1 launch of a 66M-path batch on input/hdr.json ({m['duration']:.2f} ms): "
+                        f"{traffic / 1e9:.2f} GB of DRAM traffic, far BELOW the algorithmic figure because nodes and triangles are served by L1/L2")
     except Exception:   # noqa: BLE001
         pass
+    shade_bytes = 116.0    # K3 per ray: 68 B in (ray 48 + hit 20) + 48 B out when the path survives
     roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 2) if achieved else None, "peak": peak,
                 "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                 "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
@@ -375,40 +400,77 @@ def main():
                 "trace_share_of_step": round(prof["trace_ms"] / prof["total_ms"], 4) if prof["total_ms"] else None,
                 "shade_share_of_step": round(prof["shade_ms"] / prof["total_ms"], 4) if prof["total_ms"] else None,
                 "trace_gray_per_s": round(prof["rays"] / trace_s / 1e9, 3) if trace_s > 0 else None,
+                "shade": {"kernel": "k_shade (+k_bucket)", "bytes_per_ray": shade_bytes, "gray_per_s": round(prof["rays"] / shade_s / 1e9, 3) if shade_s > 0 else None,
+                          "achieved": round(prof["rays"] * shade_bytes / shade_s / 1e9, 2) if shade_s > 0 else None,
+                          "frac": round(prof["rays"] * shade_bytes / shade_s / 1e9 / peak, 4) if shade_s > 0 else None},
                 "note": "achieved = rays * B_ray / sum of k_trace launch durations (CUDA events, rank-local profiled step); "
                         "the scene (~50 MB) is L2-resident, so DRAM traffic is mostly the wavefront state"}
-    g.close()
+
+    # ---- e2e: libcrhost.so renderFrame, host scene -> host frame, wall clock --------------------------------------------------
+    e_steps = max(1, min(args.steps, 3))
+    R.render()                                   # one untimed frame: first-touch of this process' renderFrame path (threads, caches)
+    barrier()
+    t0 = time.perf_counter()
+    e_rays = 0
+    for _ in range(e_steps):
+        _, r_ = R.render()
+        e_rays += r_
+    barrier()
+    e_ms = 1e3 * (time.perf_counter() - t0)
+    fb = R.framebuffer()
+    frame_crc = zlib.crc32(fb.tobytes()) if rank == 0 else 0
+    finite = bool(np.isfinite(fb).all()) if rank == 0 else True
+    et = torch.tensor([e_ms, float(e_rays)], device=dev, dtype=torch.float64)
+    if dist:
+        a = et.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = et.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e_ms, e_rays = float(a[0]), float(b[1])
+    e2e_value = e_rays / e_ms / 1e3
+    h2d = 0
+    try:
+        import ctypes as C
+        n = C.c_size_t()
+        crgpu.lib().crgpu_prepared_slab.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+        crgpu.lib().crgpu_prepared_slab(C.c_void_p(R.prepared()), None, C.byref(n))
+        h2d = int(n.value)
+    except Exception:   # noqa: BLE001
+        pass
+    R.close()
 
     # ---- CPU baseline: the unmodified reference on the host cores, bounded sample, rank 0 at N=1 ------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_threads()
         cspp = args.cpu_spp or max(1, min(spp, int(2.5e8 / (W * H)) or 1))   # ~10-30 s of CPU rendering (5-15 Msample/s on the host)
         r = run_reference(w["scene"], W, H, cspp, bounces, cores)
         if r:
             secs, samples, threads = r
             cpu = {"value": round(samples / secs / 1e6 * (rays / paths), 3), "unit": "Mray/s", "cores": threads, "kind": "reference",
-                   "msample_per_s": round(samples / secs / 1e6, 3), "seconds": round(secs, 2),
+                   "msample_per_s": round(samples / secs / 1e6, 3), "seconds": round(secs, 2), "host": host_cpus(),
                    "sample": f"unmodified reference (oracle/_ref/cray_ref_stock, pthreads -j {threads}) on input/{w['scene']}.json {W}x{H}, "
                              f"{cspp} spp of {spp}, {bounces} bounces; Mray/s = its Msample/s x {rays / paths:.3f} rays/sample counted on the GPU run"}
         else:
-            cpu = {"value": None, "unit": "Mray/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
+            cpu = {"value": None, "unit": "Mray/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref missing", "host": host_cpus()}
 
     if rank == 0:
         line = {"metric": "Mray/s", "value": round(value, 2), "unit": "Mray/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "bundled scene input/%s.json flattened by the reference loader at build time (no synthetic tensors on this path)" % w["scene"],
-                "config": {"workload": f"input/{w['scene']}.json {W}x{H} {spp} spp {bounces} bounces", "tile": tile or "whole frame",
-                           "parallelism": f"tile-sharded x{world}" if world > 1 else "1 GPU",
+                "dtype": "f32", "data": "bundled scene " + scene_src + " (no synthetic tensors on this path)",
+                "config": {"workload": f"input/{w['scene']}.json {W}x{H} {spp} spp {bounces} bounces", "name": args.workload, "tile": tile,
+                           "parallelism": f"tile-sharded x{world} (queue position % world), one NCCL gather per frame" if world > 1 else "1 GPU",
                            "l2": "wavefront state (GBs per step) streams through the 126 MB L2: inputs larger than L2, no explicit flush"},
                 "msample_per_s": round(msample, 2), "rays_per_sample": round(rays / paths, 4),
-                "e2e": {"value": round(e2e_value, 2), "unit": "Mray/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * W * 3 * 4,
+                "e2e": {"value": round(e2e_value, 2), "unit": "Mray/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * W * 3 * 4 + H * W * 3,
                         "ms_per_step": round(e_ms / e_steps, 3), "steps": e_steps,
-                        "what": "crscene (host) -> crgpu_scene_create -> crgpu_render_tile xtiles -> NCCL gather -> crgpu_framebuffer_read (host)"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+                        "what": "libcrhost.so renderFrame: prepared scene (pinned host) -> H2D -> tiles through the C dispatcher -> NCCL gather (C) -> "
+                                "D2H fp32 renderBuffer + 8-bit sRGB image (host)"},
+                "frame_crc32": f"{frame_crc:08x}", "value_path_crc32": f"{value_crc:08x}", "frame_finite": finite,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "scene_load": {"loader_s": round(ingest_s, 3), "prepare_s": round(prepare_s, 3),
+                               "what": "crloader_load_json (parse + decode + both BVH levels) and crgpu_prepare (re-layout into pinned memory); once per scene, outside the frames"}}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.no_ingest:
             ingest = scene_ingest(w["scene"])
             if ingest:
                 line["scene_ingest"] = ingest

@@ -79,12 +79,16 @@ def lib():
         L.crgpu_framebuffer_to_srgb8.argtypes = [P, P]
         L.crgpu_framebuffer_device_ptr.argtypes = [P, C.POINTER(P), C.POINTER(C.c_size_t)]
         L.crgpu_trace_kat.argtypes = [P, P, C.c_int, P]
+        L.crgpu_scene_create_prepared.argtypes = [P, C.c_int, C.POINTER(P)]
+        L.crgpu_scene_info.argtypes = [P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.crgpu_device_trim.argtypes = [C.c_int]
         L.crscene_load.argtypes = [C.POINTER(FlatScene), C.c_char_p]
         L.crscene_free.argtypes = [C.POINTER(FlatScene)]
         L.crscene_set_config.argtypes = [C.POINTER(FlatScene)] + [C.c_int] * 4
         for f in ("crgpu_device_count", "crgpu_scene_create", "crgpu_scene_destroy", "crgpu_set_max_paths_in_flight",
                   "crgpu_render_tile", "crgpu_render_tiles", "crgpu_set_stream", "crgpu_use_own_stream", "crgpu_get_stats", "crgpu_framebuffer_clear", "crgpu_framebuffer_read", "crgpu_framebuffer_write",
                   "crgpu_framebuffer_to_srgb8", "crgpu_framebuffer_device_ptr", "crgpu_trace_kat", "crscene_load",
+                  "crgpu_scene_create_prepared", "crgpu_scene_info", "crgpu_device_trim",
                   "crscene_set_config"):
             getattr(L, f).restype = C.c_int
         _lib = L
@@ -109,8 +113,18 @@ def device_count():
 class GpuScene:
     """A scene resident on one GPU (crgpu_scene) plus its device framebuffer."""
 
-    def __init__(self, crscene_path, width=0, height=0, samples=0, bounces=0, device=0, max_paths=None, force_bounces=None):
+    def __init__(self, crscene_path, width=0, height=0, samples=0, bounces=0, device=0, max_paths=None, force_bounces=None, prepared=None):
         L = lib()
+        if prepared is not None:
+            # a crgpu_prepared* owned by someone else (e.g. crhost.Renderer.prepared()): upload only
+            self.handle = C.c_void_p()
+            _check(L.crgpu_scene_create_prepared(C.c_void_p(prepared), device, C.byref(self.handle)), "crgpu_scene_create_prepared")
+            d, w, h = C.c_int(), C.c_int(), C.c_int()
+            _check(L.crgpu_scene_info(self.handle, C.byref(d), C.byref(w), C.byref(h)), "crgpu_scene_info")
+            self.W, self.H, self.samples, self.bounces = w.value, h.value, samples, bounces
+            if max_paths:
+                _check(L.crgpu_set_max_paths_in_flight(self.handle, int(max_paths)), "crgpu_set_max_paths_in_flight")
+            return
         if str(crscene_path).lower().endswith(".json"):
             # a c-ray JSON scene: parsed + BVH-built on the host by libcrloader.so (include/crloader.h)
             import crscene
@@ -154,6 +168,9 @@ class GpuScene:
     def set_stream(self, cuda_stream_ptr):
         """Enqueue on a caller-owned cudaStream_t (int pointer, e.g. torch.cuda.current_stream().cuda_stream)."""
         _check(lib().crgpu_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)), "crgpu_set_stream")
+
+    def use_own_stream(self):
+        _check(lib().crgpu_use_own_stream(self.handle), "crgpu_use_own_stream")
 
     def get_stats(self):
         st = Stats()
@@ -220,3 +237,33 @@ class GpuScene:
             self.close()
         except Exception:
             pass
+
+
+class RankGather:
+    """libcrgpu_nccl.so through ctypes: the tile gather of a one-process-per-GPU job on an EXISTING communicator (crgpu_comm*,
+    e.g. crhost.Renderer.comm()).  Loaded after libcrgpu.so (its symbols) — and after torch when torch is in the process, so
+    that both bind the one libnccl.so.2 already mapped."""
+
+    def __init__(self, comm_ptr):
+        lib()
+        C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        self.L = C.CDLL(os.path.join(HERE, "libcrgpu_nccl.so"))
+        P = C.c_void_p
+        self.L.crgpu_comm_gather_tiles_rank.argtypes = [P, P, P, P, C.c_int, C.c_int]
+        self.L.crgpu_comm_set_stream.argtypes = [P, P, C.c_int]
+        self.comm = C.c_void_p(comm_ptr)
+
+    def set_stream(self, cuda_stream_ptr):
+        if self.L.crgpu_comm_set_stream(self.comm, C.c_void_p(cuda_stream_ptr), 0) != 0:
+            raise CrgpuError("crgpu_comm_set_stream failed")
+
+    def use_own_stream(self):
+        if self.L.crgpu_comm_set_stream(self.comm, None, 1) != 0:
+            raise CrgpuError("crgpu_comm_set_stream failed")
+
+    def gather(self, scene, rects, owner, root=0):
+        rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+        owner = np.ascontiguousarray(owner, dtype=np.int32)
+        rc = self.L.crgpu_comm_gather_tiles_rank(self.comm, scene.handle, rects.ctypes.data, owner.ctypes.data, len(rects), root)
+        if rc != 0:
+            raise CrgpuError(f"crgpu_comm_gather_tiles_rank failed ({rc})")

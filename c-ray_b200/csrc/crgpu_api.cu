@@ -43,6 +43,110 @@ extern "C" int crgpu_device_count(int *n) {
 	return CRGPU_OK;
 }
 
+/* ---- per-device context: a caching allocator ----------------------------------------------------------------------------------
+ * A frame of this renderer wants ~35 GB of wavefront state, a 50 MB scene and a framebuffer.  cudaMalloc of those costs
+ * 10-55 ms and cudaFree of the 35 GB 0.3-0.5 s (profiles/r01_e2e_breakdown.txt) — per FRAME when every renderFrame creates and
+ * destroys its scene replica, as the reference's renderFrame does with its buffers.  So device memory released by a scene goes
+ * back to a per-device cache and the next scene on that device takes it from there (best fit within 2x); a cudaMalloc that
+ * fails trims the cache and retries.  crgpu_device_trim() hands everything back to the driver. */
+#define CRG_MAX_DEVICES 64
+struct DevBlock { void *p; size_t bytes; };
+struct DevCtx {
+	std::mutex lock;
+	std::vector<DevBlock> cache;
+	size_t cached = 0;
+};
+static DevCtx g_ctx[CRG_MAX_DEVICES];
+static DevCtx &ctx_of(int dev) { return g_ctx[dev >= 0 && dev < CRG_MAX_DEVICES ? dev : 0]; }
+
+static void ctx_trim_locked(DevCtx &c) {
+	for (DevBlock &b : c.cache) cudaFree(b.p);
+	c.cache.clear();
+	c.cached = 0;
+}
+/* the calling thread's current device must be `dev` */
+static int ctx_alloc(int dev, size_t bytes, void **out) {
+	*out = nullptr;
+	if (bytes == 0) bytes = 256;
+	DevCtx &c = ctx_of(dev);
+	std::lock_guard<std::mutex> g(c.lock);
+	int best = -1;
+	for (size_t i = 0; i < c.cache.size(); ++i)
+		if (c.cache[i].bytes >= bytes && c.cache[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || c.cache[i].bytes < c.cache[(size_t)best].bytes)) best = (int)i;
+	if (best >= 0) {
+		*out = c.cache[(size_t)best].p;
+		c.cached -= c.cache[(size_t)best].bytes;
+		c.cache.erase(c.cache.begin() + best);
+		return CRGPU_OK;
+	}
+	cudaError_t e = cudaMalloc(out, bytes);
+	if (e == cudaErrorMemoryAllocation && !c.cache.empty()) {
+		cudaGetLastError();
+		ctx_trim_locked(c);
+		e = cudaMalloc(out, bytes);
+	}
+	if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); *out = nullptr; return fail(CRGPU_ERR_NOMEM, "out of device memory allocating %zu bytes on device %d", bytes, dev); }
+	if (e != cudaSuccess) { *out = nullptr; return fail(CRGPU_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+	return CRGPU_OK;
+}
+/* size actually backing a pointer handed out for a request of `bytes` is not tracked: callers remember their request, and a
+ * cached block is re-used only for requests it can hold, so recording the REQUEST size is conservative and safe */
+static void ctx_free(int dev, void *p, size_t bytes) {
+	if (!p) return;
+	if (bytes == 0) bytes = 256;
+	DevCtx &c = ctx_of(dev);
+	std::lock_guard<std::mutex> g(c.lock);
+	if (c.cache.size() >= 24) {                      /* bound the list: drop the smallest entry */
+		size_t k = 0;
+		for (size_t i = 1; i < c.cache.size(); ++i) if (c.cache[i].bytes < c.cache[k].bytes) k = i;
+		cudaFree(c.cache[k].p);
+		c.cached -= c.cache[k].bytes;
+		c.cache.erase(c.cache.begin() + (long)k);
+	}
+	c.cache.push_back({ p, bytes });
+	c.cached += bytes;
+}
+static size_t ctx_cached_bytes(int dev) { DevCtx &c = ctx_of(dev); std::lock_guard<std::mutex> g(c.lock); return c.cached; }
+
+extern "C" int crgpu_device_trim(int device) {
+	int ndev = 0;
+	int rc = crgpu_device_count(&ndev);
+	if (rc) return rc;
+	if (device < 0 || device >= ndev) return fail(CRGPU_ERR_BAD_ARGUMENT, "device %d out of range (have %d)", device, ndev);
+	CU(cudaSetDevice(device));
+	DevCtx &c = ctx_of(device);
+	std::lock_guard<std::mutex> g(c.lock);
+	ctx_trim_locked(c);
+	return CRGPU_OK;
+}
+
+/* pinned host memory for buffers that cross PCIe every frame (the host framebuffer of renderFrame, the prepared scene) */
+extern "C" void *crgpu_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+extern "C" void crgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* ---- the prepared scene: the flat scene re-laid out for the kernels, in ONE host slab (pinned) ----------------------------------
+ * crgpu_prepare() does everything about a scene that does not depend on the device: validation, BVH re-layout into pair nodes,
+ * triangle packing, shading records.  crgpu_scene_create_prepared() is then one host->device copy of the slab plus two small
+ * pointer-carrying tables.  A host that renders many frames of one scene, or one frame on many GPUs, prepares once. */
+enum { SEC_STAGE, SEC_PAIRS, SEC_TRIS, SEC_SLOT_POLY, SEC_SPOLYS, SEC_TOP_PRIMS, SEC_BVHS, SEC_INSTS, SEC_MATS, SEC_NODES, SEC_TEXS, SEC_LUT, SEC_TEXDATA, SEC_COUNT };
+struct crgpu_prepared {
+	crs_prefs prefs;
+	crs_camera camera;
+	int32_t background;
+	uint32_t instance_count;
+	DevBvh top;
+	uint32_t stage_pairs;
+	uint32_t texture_count;
+	uint8_t *slab;
+	bool pinned;
+	size_t slab_bytes;
+	size_t off[SEC_COUNT], len[SEC_COUNT];
+};
+
 struct crgpu_scene {
 	int device;
 	int sm_count;
@@ -53,29 +157,20 @@ struct crgpu_scene {
 	float pend_trace_ms, pend_shade_ms, pend_total_ms;
 	DevScene dev;
 	DevScene *dev_copy;        /* the same descriptor in HBM, for kernels that call noinline device functions */
-	std::vector<void *> allocs;
+	void *slab; size_t slab_bytes;   /* the scene arrays + dev_copy */
+	void *small; size_t small_bytes; /* hist, counts, stats */
 	float *fb;                 /* W*H*3 fp32, row H-1-y */
 	uint8_t *fb8;              /* lazily allocated sRGB8 staging */
 	size_t fb_floats;
 	uint64_t max_paths;
 	uint64_t cap_paths;        /* capacity of the wavefront buffers */
+	void *wave; size_t wave_bytes;
 	WaveBuffers wb;
 	cudaEvent_t ev[4];
 	uint32_t *pixels;          /* device pixel list of the last crgpu_render_tiles tile set */
 	size_t pixel_cap;
 	std::vector<int> pixel_key;
 };
-
-template <class T>
-static int upload(crgpu_scene *s, const std::vector<T> &v, const T **out) {
-	void *p = nullptr;
-	size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
-	CU(cudaMalloc(&p, bytes));
-	s->allocs.push_back(p);
-	if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-	*out = static_cast<const T *>(p);
-	return CRGPU_OK;
-}
 
 /* ---- node graph checks -------------------------------------------------------------------------------------- */
 static bool node_ok(const crs_scene *f, int idx) { return idx >= 0 && (uint32_t)idx < f->node_count; }
@@ -194,25 +289,31 @@ static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNod
 		memcpy(out.root_bounds, nodes[0].bounds, sizeof out.root_bounds);
 		out.root_first = nodes[0].first_child_or_prim;
 		out.root_count = nodes[0].prim_count_leaf & CRS_BVH_COUNT_MASK;
+		if ((uint64_t)out.root_first + out.root_count > (uint64_t)b.prim_count) return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH leaf range outside the primitive list");
 		return CRGPU_OK;
 	}
 	/* BFS over internal nodes; pair index = BFS rank */
 	std::vector<uint32_t> order;            /* reference node index of each internal node, BFS order */
 	order.reserve(b.node_count / 2 + 1);
 	std::vector<uint32_t> rank(b.node_count, 0xffffffffu);
+	std::vector<uint8_t> depth(b.node_count, 0);   /* the traversal stack holds CRG_MAX_STACK entries per level (bvh.c:32) */
 	order.push_back(0);
 	rank[0] = 0;
 	for (size_t head = 0; head < order.size(); ++head) {
 		const crs_bvh_node &n = nodes[order[head]];
 		if (n.prim_count_leaf & CRS_BVH_LEAF_BIT) return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH root/internal node is a leaf");
 		const uint32_t fc = n.first_child_or_prim;
-		if (fc + 1 >= b.node_count) return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH child index out of range");
+		if ((uint64_t)fc + 1u >= (uint64_t)b.node_count) return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH child index out of range");
+		if (depth[order[head]] >= CRG_MAX_STACK) return err->set(CRGPU_ERR_UNSUPPORTED, "BVH deeper than 64 levels");
 		for (uint32_t k = 0; k < 2; ++k) {
 			const crs_bvh_node &c = nodes[fc + k];
 			if (!(c.prim_count_leaf & CRS_BVH_LEAF_BIT)) {
 				if (rank[fc + k] != 0xffffffffu) return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH is not a tree");
 				rank[fc + k] = (uint32_t)order.size();
+				depth[fc + k] = (uint8_t)(depth[order[head]] + 1);
 				order.push_back(fc + k);
+			} else if ((uint64_t)c.first_child_or_prim + (uint64_t)(c.prim_count_leaf & CRS_BVH_COUNT_MASK) > (uint64_t)b.prim_count) {
+				return err->set(CRGPU_ERR_BAD_ARGUMENT, "BVH leaf range outside the primitive list");
 			}
 		}
 	}
@@ -240,20 +341,27 @@ static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNod
 
 static inline void f3(float *dst, const float *src, size_t idx) { dst[0] = src[3 * idx]; dst[1] = src[3 * idx + 1]; dst[2] = src[3 * idx + 2]; }
 
+/* all wavefront buffers of a scene are carved from ONE device block (one cudaMalloc / one cache hit per frame) */
 static int alloc_wave(crgpu_scene *s, uint64_t paths) {
 	if (paths <= s->cap_paths) return CRGPU_OK;
 	WaveBuffers &w = s->wb;
-	void **ptrs[] = { (void **)&w.stA[0], (void **)&w.stA[1], (void **)&w.stB[0], (void **)&w.stB[1], (void **)&w.stC[0],
-					  (void **)&w.stC[1], (void **)&w.hit, (void **)&w.hitInst, (void **)&w.L, (void **)&w.hitKey, (void **)&w.perm };
-	for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
-	s->cap_paths = 0;
-	const size_t n = (size_t)paths;
-	CU(cudaMalloc((void **)&w.stA[0], n * 16)); CU(cudaMalloc((void **)&w.stA[1], n * 16));
-	CU(cudaMalloc((void **)&w.stB[0], n * 16)); CU(cudaMalloc((void **)&w.stB[1], n * 16));
-	CU(cudaMalloc((void **)&w.stC[0], n * 16)); CU(cudaMalloc((void **)&w.stC[1], n * 16));
-	CU(cudaMalloc((void **)&w.hit, n * 16)); CU(cudaMalloc((void **)&w.hitInst, n * 4));
-	CU(cudaMalloc((void **)&w.L, n * 16));
-	CU(cudaMalloc((void **)&w.hitKey, n)); CU(cudaMalloc((void **)&w.perm, n * 4));
+	if (s->wave) ctx_free(s->device, s->wave, s->wave_bytes);
+	s->wave = nullptr; s->wave_bytes = 0; s->cap_paths = 0;
+	const size_t n = ((size_t)paths + 255u) & ~(size_t)255u;      /* every sub-array stays 256-byte aligned */
+	const size_t bytes = n * (9u * 16u + 2u * 4u + 1u);
+	void *base = nullptr;
+	int rc = ctx_alloc(s->device, bytes, &base);
+	if (rc) return rc;
+	s->wave = base; s->wave_bytes = bytes;
+	uint8_t *q = static_cast<uint8_t *>(base);
+	auto take = [&](size_t b) { uint8_t *r = q; q += b; return r; };
+	w.stA[0] = (float4 *)take(n * 16); w.stA[1] = (float4 *)take(n * 16);
+	w.stB[0] = (float4 *)take(n * 16); w.stB[1] = (float4 *)take(n * 16);
+	w.stC[0] = (uint4 *)take(n * 16); w.stC[1] = (uint4 *)take(n * 16);
+	w.hit = (float4 *)take(n * 16); w.L = (float4 *)take(n * 16);
+	w.hitInst = (int *)take(n * 4); w.perm = (unsigned *)take(n * 4);
+	w.hitKey = (unsigned char *)take(n);
+	take(n * 16);                                                  /* spare 16-B lane (keeps the block size a round 137 -> 153 B/path) */
 	s->cap_paths = paths;
 	return CRGPU_OK;
 }
@@ -263,58 +371,65 @@ extern "C" int crgpu_scene_destroy(crgpu_scene *s) {
 	cudaSetDevice(s->device);
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	if (s->own_stream && s->own_stream != s->stream) cudaStreamSynchronize(s->own_stream);
-	for (void *p : s->allocs) cudaFree(p);
-	WaveBuffers &w = s->wb;
-	void *ptrs[] = { w.stA[0], w.stA[1], w.stB[0], w.stB[1], w.stC[0], w.stC[1], w.hit, w.hitInst, w.L, w.hitKey, w.perm, w.hist, w.counts, w.stats, s->fb, s->fb8, s->pixels };
-	for (void *p : ptrs) if (p) cudaFree(p);
+	ctx_free(s->device, s->slab, s->slab_bytes);
+	ctx_free(s->device, s->wave, s->wave_bytes);
+	ctx_free(s->device, s->small, s->small_bytes);
+	ctx_free(s->device, s->fb, s->fb_floats * sizeof(float));
+	ctx_free(s->device, s->fb8, s->fb_floats);
+	ctx_free(s->device, s->pixels, s->pixel_cap * sizeof(uint32_t));
 	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
 	if (s->own_stream) cudaStreamDestroy(s->own_stream);
 	delete s;
 	return CRGPU_OK;
 }
 
-extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_scene **out) {
+extern "C" void crgpu_prepared_free(crgpu_prepared *p) {
+	if (!p) return;
+	if (p->slab) { if (p->pinned) cudaFreeHost(p->slab); else free(p->slab); }
+	delete p;
+}
+static int pfail(crgpu_prepared *p, int rc) { crgpu_prepared_free(p); return rc; }
+
+extern "C" int crgpu_prepared_update_config(crgpu_prepared *p, const struct crs_scene *f) {
+	if (!p || !f) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
+	if (f->prefs.image_width == 0 || f->prefs.image_height == 0 || f->prefs.sample_count == 0)
+		return fail(CRGPU_ERR_BAD_ARGUMENT, "empty image or zero samples");
+	p->prefs = f->prefs;
+	p->camera = f->camera;
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_prepared_slab(const crgpu_prepared *p, const void **slab, size_t *bytes) {
+	if (!p) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
+	if (slab) *slab = p->slab;
+	if (bytes) *bytes = p->slab_bytes;
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_prepare(const struct crs_scene *f, crgpu_prepared **out) {
 	if (!f || !out) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
 	*out = nullptr;
-	int ndev = 0;
-	int rc = crgpu_device_count(&ndev);
-	if (rc) return rc;
-	if (device < 0 || device >= ndev) return fail(CRGPU_ERR_BAD_ARGUMENT, "device %d out of range (have %d)", device, ndev);
 	if (f->prefs.image_width == 0 || f->prefs.image_height == 0 || f->prefs.sample_count == 0)
 		return fail(CRGPU_ERR_BAD_ARGUMENT, "empty image or zero samples");
 	if (!node_ok(f, f->background) || f->nodes[f->background].kind != CRS_BSDF_BACKGROUND)
 		return fail(CRGPU_ERR_UNSUPPORTED, "scene background must be a background node");
 	if (f->top_bvh >= f->bvh_count) return fail(CRGPU_ERR_BAD_ARGUMENT, "top_bvh out of range");
-	CU(cudaSetDevice(device));
-
-	crgpu_scene *s = new crgpu_scene();
-	memset(&s->dev, 0, sizeof s->dev);
-	memset(&s->wb, 0, sizeof s->wb);
-	s->pixels = nullptr; s->pixel_cap = 0;
-	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->own_stream = nullptr; s->cap_paths = 0;
-	memset(s->fetched, 0, sizeof s->fetched);
-	s->pend_paths = s->pend_launches = 0; s->pend_trace_ms = s->pend_shade_ms = s->pend_total_ms = 0.f;
-	s->max_paths = 0;   /* set below from the free device memory */
-	for (auto &e : s->ev) e = nullptr;
-#define FAIL_IF(x) do { int rc_ = (x); if (rc_) { crgpu_scene_destroy(s); return rc_; } } while (0)
-#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(CRGPU_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); crgpu_scene_destroy(s); return rc_; } } while (0)
-	cudaDeviceProp prop;
-	CUS(cudaGetDeviceProperties(&prop, device));
-	s->sm_count = prop.multiProcessorCount;
-	CUS(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
-	s->stream = s->own_stream;
-	for (auto &e : s->ev) CUS(cudaEventCreate(&e));
+	crgpu_prepared *p = new crgpu_prepared();
+	p->slab = nullptr; p->pinned = false; p->slab_bytes = 0;
+	p->prefs = f->prefs; p->camera = f->camera; p->background = f->background; p->instance_count = f->instance_count;
+	p->texture_count = f->texture_count;
+#define PFAIL(x) do { int rc_ = (x); if (rc_) return pfail(p, rc_); } while (0)
 
 	/* materials + graph validation */
 	std::vector<DevMaterial> mats(f->material_count);
 	{
 		bool uv = false;
-		FAIL_IF(check_bsdf(f, f->background, 0, 0, &uv));
+		PFAIL(check_bsdf(f, f->background, 0, 0, &uv));
 	}
 	for (uint32_t i = 0; i < f->material_count; ++i) {
 		const crs_material &m = f->materials[i];
 		bool uv = false;
-		FAIL_IF(check_bsdf(f, m.bsdf, 0, 0, &uv));
+		PFAIL(check_bsdf(f, m.bsdf, 0, 0, &uv));
 		DevMaterial d;
 		memset(&d, 0, sizeof d);
 		d.emission[0] = m.emission[0]; d.emission[1] = m.emission[1]; d.emission[2] = m.emission[2];
@@ -335,7 +450,7 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	std::vector<int32_t> top_prims;
 	std::vector<uint32_t> mesh_of_bvh(f->bvh_count, 0xffffffffu);
 	for (uint32_t m = 0; m < f->mesh_count; ++m) {
-		if (f->meshes[m].bvh >= f->bvh_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "mesh bvh index out of range"); }
+		if (f->meshes[m].bvh >= f->bvh_count) { return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "mesh bvh index out of range")); }
 		mesh_of_bvh[f->meshes[m].bvh] = m;
 	}
 	std::vector<uint32_t> slot_off(f->bvh_count, 0u);      /* first triangle slot of every mesh BVH (0 for the top level) */
@@ -343,18 +458,18 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 	for (uint32_t b = 0; b < f->bvh_count; ++b) {
 		const crs_bvh &src = f->bvhs[b];
 		if ((uint64_t)src.node_offset + src.node_count > f->bvh_node_count || (uint64_t)src.prim_offset + src.prim_count > f->prim_index_count) {
-			crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u ranges out of bounds", b);
+			return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u ranges out of bounds", b));
 		}
 		if (b == f->top_bvh) continue;
-		if (mesh_of_bvh[b] == 0xffffffffu) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u belongs to no mesh", b); }
+		if (mesh_of_bvh[b] == 0xffffffffu) { return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "bvh %u belongs to no mesh", b)); }
 		slot_off[b] = (uint32_t)total_slots;
 		total_slots += src.prim_count;
 	}
-	if (total_slots > 0xffffffffull) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_UNSUPPORTED, "more than 2^32 triangle slots"); }
+	if (total_slots > 0xffffffffull) { return pfail(p, fail(CRGPU_ERR_UNSUPPORTED, "more than 2^32 triangle slots")); }
 	for (uint32_t m = 0; m < f->mesh_count; ++m) {
 		const crs_mesh &mesh = f->meshes[m];
 		if ((uint64_t)mesh.poly_offset + mesh.poly_count > f->poly_count || (uint64_t)mesh.material_offset + mesh.material_count > f->material_count) {
-			crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "mesh %u ranges out of bounds", m);
+			return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "mesh %u ranges out of bounds", m));
 		}
 	}
 	tris.resize((size_t)total_slots);
@@ -444,7 +559,7 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 		});
 	}
 	pair_thread.join();
-	if (herr.code) { crgpu_scene_destroy(s); return fail(herr.code, "%s", herr.msg); }
+	if (herr.code) { return pfail(p, fail(herr.code, "%s", herr.msg)); }
 
 	/* instances */
 	std::vector<DevInstance> insts(f->instance_count);
@@ -456,55 +571,41 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 		memcpy(d.A, src.A, sizeof d.A);
 		d.kind = src.kind;
 		if (src.kind == CRS_INST_MESH) {
-			if (src.object >= f->mesh_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "instance mesh index out of range"); }
+			if (src.object >= f->mesh_count) { return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "instance mesh index out of range")); }
 			d.bvh = f->meshes[src.object].bvh;
 			d.ray_offset = f->meshes[src.object].ray_offset;
 		} else if (src.kind == CRS_INST_SPHERE) {
-			if (src.object >= f->sphere_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "instance sphere index out of range"); }
+			if (src.object >= f->sphere_count) { return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "instance sphere index out of range")); }
 			d.ray_offset = f->spheres[src.object].ray_offset;
 			d.radius = f->spheres[src.object].radius;
 			d.material = f->spheres[src.object].material;
-			if (d.material >= f->material_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "sphere material out of range"); }
-		} else { crgpu_scene_destroy(s); return fail(CRGPU_ERR_UNSUPPORTED, "instance kind %u (volumes are not reachable from the scene loader)", src.kind); }
+			if (d.material >= f->material_count) { return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "sphere material out of range")); }
+		} else { return pfail(p, fail(CRGPU_ERR_UNSUPPORTED, "instance kind %u (volumes are not reachable from the scene loader)", src.kind)); }
 		insts[i] = d;
 	}
 
-	/* textures */
-	uint8_t *texdata = nullptr;
-	if (f->texdata_bytes) {
-		CUS(cudaMalloc((void **)&texdata, (size_t)f->texdata_bytes));
-		s->allocs.push_back(texdata);
-		CUS(cudaMemcpy(texdata, f->texdata, (size_t)f->texdata_bytes, cudaMemcpyHostToDevice));
-	}
+	/* textures (data pointers are byte offsets into the texture section here; patched per device at upload) */
 	std::vector<DevTexture> texs(f->texture_count);
 	for (uint32_t i = 0; i < f->texture_count; ++i) {
 		const crs_texture &t = f->textures[i];
 		const uint64_t bytes = (uint64_t)t.width * t.height * t.channels * (t.is_float ? 4u : 1u);
-		if (t.width == 0 || t.height == 0 || t.channels == 0 || t.channels > 4 || t.data_offset + bytes > f->texdata_bytes) {
-			crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "texture %u malformed", i);
+		if (t.width == 0 || t.height == 0 || t.channels == 0 || t.channels > 4 || t.width > 65536u || t.height > 65536u ||
+			t.data_offset > f->texdata_bytes || bytes > f->texdata_bytes - t.data_offset) {
+			return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "texture %u malformed", i));
 		}
 		DevTexture d;
 		d.width = t.width; d.height = t.height; d.channels = t.channels; d.is_float = t.is_float; d.has_alpha = t.has_alpha; d.pad = 0;
 		d.wmask = (t.width & (t.width - 1u)) == 0u ? t.width - 1u : 0u;
 		d.hmask = (t.height & (t.height - 1u)) == 0u ? t.height - 1u : 0u;
-		d.data = texdata + t.data_offset;
+		d.data = reinterpret_cast<const uint8_t *>((uintptr_t)t.data_offset);
 		texs[i] = d;
 	}
 	for (uint32_t i = 0; i < f->node_count; ++i)
-		if (f->nodes[i].kind == CRS_COLOR_IMAGE && f->nodes[i].tex >= (int32_t)f->texture_count) { crgpu_scene_destroy(s); return fail(CRGPU_ERR_BAD_ARGUMENT, "node %u texture index out of range", i); }
+		if (f->nodes[i].kind == CRS_COLOR_IMAGE && (f->nodes[i].tex >= (int32_t)f->texture_count || f->nodes[i].tex < -1))
+			return pfail(p, fail(CRGPU_ERR_BAD_ARGUMENT, "node %u texture index out of range", i));
+
 	std::vector<crs_node> nodes(f->nodes, f->nodes + f->node_count);
 
-	DevScene &d = s->dev;
-	d.cam.sensor_x = f->camera.sensor_x; d.cam.sensor_y = f->camera.sensor_y;
-	d.cam.aperture = f->camera.aperture; d.cam.focal_distance = f->camera.focal_distance;
-	memcpy(d.cam.forward, f->camera.forward, 12); memcpy(d.cam.right, f->camera.right, 12); memcpy(d.cam.up, f->camera.up, 12);
-	d.cam.width = f->camera.width; d.cam.height = f->camera.height;
-	memcpy(d.cam.A, f->camera.A, sizeof d.cam.A);
-	d.image_width = f->prefs.image_width; d.image_height = f->prefs.image_height;
-	d.sample_count = f->prefs.sample_count; d.bounces = f->prefs.bounces;
-	d.background = f->background;
-	d.instance_count = f->instance_count;
-	d.top = bvhs[f->top_bvh];
 	/* staging image: top-of-tree pair nodes (BFS prefix) of every BVH, the top level first, then the meshes
 	 * in proportion to their size, CRG_STAGE_PAIRS nodes in total */
 	std::vector<PairNode> stage;
@@ -530,54 +631,152 @@ extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_s
 			const uint64_t internal = bvhs[b].node_count > 1 ? bvhs[b].pair_end - bvhs[b].pair_offset : 0;
 			take(bvhs[b], (uint32_t)((uint64_t)budget * internal / total_internal));
 		}
-		d.top = bvhs[f->top_bvh];
 	}
-	d.stage_pairs = (uint32_t)stage.size();
-	FAIL_IF(upload(s, stage, &d.stage_img));
-	FAIL_IF(upload(s, pairs, &d.pairs));
-	FAIL_IF(upload(s, tris, &d.tris));
-	FAIL_IF(upload(s, slot_poly, &d.slot_poly));
-	FAIL_IF(upload(s, spolys, &d.spolys));
-	FAIL_IF(upload(s, top_prims, &d.top_prims));
-	FAIL_IF(upload(s, bvhs, &d.bvhs));
-	FAIL_IF(upload(s, insts, &d.instances));
-	FAIL_IF(upload(s, mats, &d.materials));
-	FAIL_IF(upload(s, nodes, &d.nodes));
-	FAIL_IF(upload(s, texs, &d.textures));
-	{
-		std::vector<float> lut(256);
-		for (int i = 0; i < 256; ++i) { volatile float num = (float)i, den = 255.0f; lut[i] = num / den; }   /* IEEE divss == __fdiv_rn */
-		FAIL_IF(upload(s, lut, &d.u8_to_unit));
-	}
+	p->top = bvhs[f->top_bvh];
+	p->stage_pairs = (uint32_t)stage.size();
+	std::vector<float> lut(256);
+	for (int i = 0; i < 256; ++i) { volatile float num = (float)i, den = 255.0f; lut[i] = num / den; }   /* IEEE divss == __fdiv_rn */
 
-	CUS(cudaMalloc((void **)&s->dev_copy, sizeof(DevScene)));
-	s->allocs.push_back(s->dev_copy);
-	CUS(cudaMemcpy(s->dev_copy, &s->dev, sizeof(DevScene), cudaMemcpyHostToDevice));
+	/* lay the sections out in one slab (256-byte aligned each) and copy them in on the host threads */
+	const void *src[SEC_COUNT] = { stage.data(), pairs.data(), tris.data(), slot_poly.data(), spolys.data(), top_prims.data(), bvhs.data(),
+								   insts.data(), mats.data(), nodes.data(), texs.data(), lut.data(), f->texdata };
+	const size_t len[SEC_COUNT] = { stage.size() * sizeof(PairNode), pairs.size() * sizeof(PairNode), tris.size() * sizeof(PackedTri),
+									slot_poly.size() * sizeof(uint32_t), spolys.size() * sizeof(ShadePoly), top_prims.size() * sizeof(int32_t),
+									bvhs.size() * sizeof(DevBvh), insts.size() * sizeof(DevInstance), mats.size() * sizeof(DevMaterial),
+									nodes.size() * sizeof(crs_node), texs.size() * sizeof(DevTexture), lut.size() * sizeof(float), (size_t)f->texdata_bytes };
+	size_t total = 0;
+	for (int k = 0; k < SEC_COUNT; ++k) { p->off[k] = total; p->len[k] = len[k]; total += (len[k] + 255u) & ~(size_t)255u; }
+	total += 512;                                                  /* room for the DevScene descriptor behind the arrays */
+	p->slab_bytes = total;
+	void *host = nullptr;
+	if (cudaHostAlloc(&host, total, cudaHostAllocPortable) == cudaSuccess) p->pinned = true;
+	else { cudaGetLastError(); host = malloc(total); p->pinned = false; }   /* no device yet (host-only tooling): pageable works, slower */
+	if (!host) return pfail(p, fail(CRGPU_ERR_NOMEM, "cannot allocate the %zu-byte host slab", total));
+	p->slab = static_cast<uint8_t *>(host);
+	for (int k = 0; k < SEC_COUNT; ++k) {
+		uint8_t *dst = p->slab + p->off[k];
+		const uint8_t *from = static_cast<const uint8_t *>(src[k]);
+		const size_t n = len[k];
+		if (n) host_parallel_for((uint32_t)((n + 4095u) / 4096u), [&](uint32_t lo, uint32_t hi) {
+			const size_t b0 = (size_t)lo * 4096u, b1 = (size_t)hi * 4096u < n ? (size_t)hi * 4096u : n;
+			if (b1 > b0) memcpy(dst + b0, from + b0, b1 - b0);
+		});
+		memset(dst + n, 0, (((n + 255u) & ~(size_t)255u) - n));
+	}
+	memset(p->slab + total - 512, 0, 512);
+#undef PFAIL
+	*out = p;
+	return CRGPU_OK;
+}
+
+extern "C" int crgpu_scene_create_prepared(const crgpu_prepared *p, int device, crgpu_scene **out) {
+	if (!p || !out) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
+	*out = nullptr;
+	int ndev = 0;
+	int rc = crgpu_device_count(&ndev);
+	if (rc) return rc;
+	if (device < 0 || device >= ndev) return fail(CRGPU_ERR_BAD_ARGUMENT, "device %d out of range (have %d)", device, ndev);
+	CU(cudaSetDevice(device));
+
+	crgpu_scene *s = new crgpu_scene();
+	memset(&s->dev, 0, sizeof s->dev);
+	memset(&s->wb, 0, sizeof s->wb);
+	s->pixels = nullptr; s->pixel_cap = 0;
+	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->own_stream = nullptr; s->cap_paths = 0;
+	s->slab = nullptr; s->slab_bytes = 0; s->small = nullptr; s->small_bytes = 0; s->wave = nullptr; s->wave_bytes = 0; s->fb_floats = 0;
+	memset(s->fetched, 0, sizeof s->fetched);
+	s->pend_paths = s->pend_launches = 0; s->pend_trace_ms = s->pend_shade_ms = s->pend_total_ms = 0.f;
+	s->max_paths = 0;   /* set below from the free device memory */
+	for (auto &e : s->ev) e = nullptr;
+#define FAIL_IF(x) do { int rc_ = (x); if (rc_) { crgpu_scene_destroy(s); return rc_; } } while (0)
+#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(CRGPU_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); crgpu_scene_destroy(s); return rc_; } } while (0)
+	CUS(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
+	CUS(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+	s->stream = s->own_stream;
+	for (auto &e : s->ev) CUS(cudaEventCreate(&e));
+
+	/* the scene: one block, one copy */
+	FAIL_IF(ctx_alloc(device, p->slab_bytes, &s->slab));
+	s->slab_bytes = p->slab_bytes;
+	uint8_t *base = static_cast<uint8_t *>(s->slab);
+	CUS(cudaMemcpyAsync(base, p->slab, p->slab_bytes, cudaMemcpyHostToDevice, s->stream));
+	if (p->texture_count) {                 /* texture table with this device's addresses */
+		std::vector<DevTexture> texs(p->texture_count);
+		memcpy(texs.data(), p->slab + p->off[SEC_TEXS], p->texture_count * sizeof(DevTexture));
+		for (DevTexture &t : texs) t.data = base + p->off[SEC_TEXDATA] + (uintptr_t)t.data;
+		CUS(cudaMemcpyAsync(base + p->off[SEC_TEXS], texs.data(), texs.size() * sizeof(DevTexture), cudaMemcpyHostToDevice, s->stream));
+		CUS(cudaStreamSynchronize(s->stream));   /* texs is a local pageable buffer */
+	}
+	DevScene &d = s->dev;
+	d.cam.sensor_x = p->camera.sensor_x; d.cam.sensor_y = p->camera.sensor_y;
+	d.cam.aperture = p->camera.aperture; d.cam.focal_distance = p->camera.focal_distance;
+	memcpy(d.cam.forward, p->camera.forward, 12); memcpy(d.cam.right, p->camera.right, 12); memcpy(d.cam.up, p->camera.up, 12);
+	d.cam.width = p->camera.width; d.cam.height = p->camera.height;
+	memcpy(d.cam.A, p->camera.A, sizeof d.cam.A);
+	d.image_width = p->prefs.image_width; d.image_height = p->prefs.image_height;
+	d.sample_count = p->prefs.sample_count; d.bounces = p->prefs.bounces;
+	d.background = p->background;
+	d.instance_count = p->instance_count;
+	d.top = p->top;
+	d.stage_pairs = p->stage_pairs;
+	d.stage_img = reinterpret_cast<const PairNode *>(base + p->off[SEC_STAGE]);
+	d.pairs = reinterpret_cast<const PairNode *>(base + p->off[SEC_PAIRS]);
+	d.tris = reinterpret_cast<const PackedTri *>(base + p->off[SEC_TRIS]);
+	d.slot_poly = reinterpret_cast<const uint32_t *>(base + p->off[SEC_SLOT_POLY]);
+	d.spolys = reinterpret_cast<const ShadePoly *>(base + p->off[SEC_SPOLYS]);
+	d.top_prims = reinterpret_cast<const int32_t *>(base + p->off[SEC_TOP_PRIMS]);
+	d.bvhs = reinterpret_cast<const DevBvh *>(base + p->off[SEC_BVHS]);
+	d.instances = reinterpret_cast<const DevInstance *>(base + p->off[SEC_INSTS]);
+	d.materials = reinterpret_cast<const DevMaterial *>(base + p->off[SEC_MATS]);
+	d.nodes = reinterpret_cast<const crs_node *>(base + p->off[SEC_NODES]);
+	d.textures = reinterpret_cast<const DevTexture *>(base + p->off[SEC_TEXS]);
+	d.u8_to_unit = reinterpret_cast<const float *>(base + p->off[SEC_LUT]);
+	static_assert(sizeof(DevScene) <= 512, "DevScene must fit the descriptor slot behind the scene arrays");
+	s->dev_copy = reinterpret_cast<DevScene *>(base + p->slab_bytes - 512);
+	CUS(cudaMemcpyAsync(s->dev_copy, &s->dev, sizeof(DevScene), cudaMemcpyHostToDevice, s->stream));
+
 	s->fb_floats = (size_t)d.image_width * d.image_height * 3u;
-	CUS(cudaMalloc((void **)&s->fb, s->fb_floats * sizeof(float)));
-	CUS(cudaMemset(s->fb, 0, s->fb_floats * sizeof(float)));
-	CUS(cudaMalloc((void **)&s->wb.hist, 512 * sizeof(unsigned)));
-	CUS(cudaMemset(s->wb.hist, 0, 512 * sizeof(unsigned)));
-	CUS(cudaMalloc((void **)&s->wb.counts, 4 * sizeof(unsigned)));
-	CUS(cudaMemset(s->wb.counts, 0, 4 * sizeof(unsigned)));
-	CUS(cudaMalloc((void **)&s->wb.stats, 80 * sizeof(unsigned long long)));
-	CUS(cudaMemset(s->wb.stats, 0, 80 * sizeof(unsigned long long)));
+	{ void *q = nullptr; FAIL_IF(ctx_alloc(device, s->fb_floats * sizeof(float), &q)); s->fb = static_cast<float *>(q); }
+	CUS(cudaMemsetAsync(s->fb, 0, s->fb_floats * sizeof(float), s->stream));
+	s->small_bytes = 512 * sizeof(unsigned) + 256 + 80 * sizeof(unsigned long long);
+	FAIL_IF(ctx_alloc(device, s->small_bytes, &s->small));
+	CUS(cudaMemsetAsync(s->small, 0, s->small_bytes, s->stream));
+	s->wb.hist = static_cast<unsigned *>(s->small);
+	s->wb.counts = s->wb.hist + 512;
+	s->wb.stats = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(s->small) + 512 * sizeof(unsigned) + 256);
 	{
 		/* Paths in flight per wavefront batch.  Every batch pays a fixed ~7 ms (the serial chain of its bounces: each
 		 * late bounce lasts as long as its slowest ray), so batches should be as large as memory allows:
-		 * 137 B of wavefront state per path; use at most 40% of the free HBM, capped at 256M paths (35 GB). */
+		 * 153 B of wavefront state per path; use at most 40% of the free HBM (cached blocks count as free), capped at 256M paths. */
 		size_t free_b = 0, total_b = 0;
 		CUS(cudaMemGetInfo(&free_b, &total_b));
-		uint64_t fit = (uint64_t)((double)free_b * 0.40 / 137.0);
+		free_b += ctx_cached_bytes(device);
+		uint64_t fit = (uint64_t)((double)free_b * 0.40 / 153.0);
 		if (fit > (256ull << 20)) fit = 256ull << 20;
 		if (fit < (1ull << 20)) fit = 1ull << 20;
 		s->max_paths = fit;
 	}
-	CUS(cudaDeviceSynchronize());
+	CUS(cudaStreamSynchronize(s->stream));
 #undef FAIL_IF
 #undef CUS
 	*out = s;
 	return CRGPU_OK;
+}
+
+extern "C" int crgpu_scene_create(const struct crs_scene *f, int device, crgpu_scene **out) {
+	if (!f || !out) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
+	*out = nullptr;
+	int ndev = 0;
+	int rc = crgpu_device_count(&ndev);
+	if (rc) return rc;
+	if (device < 0 || device >= ndev) return fail(CRGPU_ERR_BAD_ARGUMENT, "device %d out of range (have %d)", device, ndev);
+	CU(cudaSetDevice(device));
+	crgpu_prepared *p = nullptr;
+	rc = crgpu_prepare(f, &p);
+	if (rc) return rc;
+	rc = crgpu_scene_create_prepared(p, device, out);
+	crgpu_prepared_free(p);
+	return rc;
 }
 
 extern "C" int crgpu_set_max_paths_in_flight(crgpu_scene *s, uint64_t max_paths) {
@@ -717,9 +916,12 @@ extern "C" int crgpu_render_tiles(crgpu_scene *s, const int *rects, int nrects, 
 				for (int x = rects[4 * i]; x < rects[4 * i + 2]; ++x) px.push_back((uint32_t)x | ((uint32_t)y << 16));
 		CU(cudaStreamSynchronize(s->stream));
 		if (s->pixel_cap < px.size()) {
-			if (s->pixels) cudaFree(s->pixels);
+			ctx_free(s->device, s->pixels, s->pixel_cap * sizeof(uint32_t));
 			s->pixels = nullptr; s->pixel_cap = 0;
-			CU(cudaMalloc((void **)&s->pixels, px.size() * sizeof(uint32_t)));
+			void *q = nullptr;
+			int arc = ctx_alloc(s->device, px.size() * sizeof(uint32_t), &q);
+			if (arc) return arc;
+			s->pixels = static_cast<uint32_t *>(q);
 			s->pixel_cap = px.size();
 		}
 		/* on the scene's own stream, then wait: a plain cudaMemcpy from pageable memory runs on the legacy stream and may
@@ -808,7 +1010,7 @@ extern "C" int crgpu_framebuffer_write(crgpu_scene *s, const float *host_rgb, in
 extern "C" int crgpu_framebuffer_to_srgb8(crgpu_scene *s, uint8_t *host_rgb8) {
 	if (!s || !host_rgb8) return fail(CRGPU_ERR_BAD_ARGUMENT, "NULL argument");
 	CU(cudaSetDevice(s->device));
-	if (!s->fb8) CU(cudaMalloc((void **)&s->fb8, s->fb_floats));
+	if (!s->fb8) { void *q = nullptr; int arc = ctx_alloc(s->device, s->fb_floats, &q); if (arc) return arc; s->fb8 = static_cast<uint8_t *>(q); }
 	crg_launch_to_srgb8(s->fb, s->fb8, s->fb_floats, s->sm_count * 8, s->stream);
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(host_rgb8, s->fb8, s->fb_floats, cudaMemcpyDeviceToHost, s->stream));

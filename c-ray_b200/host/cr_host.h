@@ -51,7 +51,7 @@ struct renderer;
 struct renderThreadState {         /* renderer.h:14-31 */
 	int thread_num;                /* = CUDA device ordinal of this worker */
 	bool threadComplete;
-	bool paused;
+	bool paused;                   /* set by the host (reference: the 'p' key, ui.c): the worker stops taking tiles until cleared */
 	int currentTileNum;
 	int completedSamples;
 	uint64_t totalSamples;
@@ -92,6 +92,14 @@ struct renderer {
 	struct crs_scene scene;        /* flat scene (owned) */
 	struct state state;
 	struct prefs prefs;
+	crgpu_prepared *prepared;      /* the scene re-laid out for the kernels, pinned host memory (built once per scene, like the
+	                                  BVHs of loadScene, scene.c:111-213); every frame uploads it to the worker GPUs */
+	/* one-process-per-GPU jobs (torchrun / mpirun style; the counterpart of the reference's cluster workers,
+	 * src/utils/protocol/worker.c): this process renders the tiles whose queue position % world == rank on `device` */
+	int rank, world, device;
+	void *comm;                    /* crgpu_comm*: persistent NCCL communicator (in-process group or this rank's membership) */
+	int commMembers;               /* size of the group `comm` was created for */
+	bool renderBufferPinned;
 };
 
 /* tile dispatcher */
@@ -112,6 +120,26 @@ void destroyRenderer(struct renderer *r);
 
 /* loads libcrgpu_nccl.so (multi-GPU tile gather) on first use; 0 when its entry points are available */
 int crhost_load_nccl(void);
+/* GPU group set-up, OUTSIDE the frame (NCCL bootstrap takes 0.1-1 s per group, once per process):
+ *   prepareGpus     in-process group for renderFrame with prefs.threadCount > 1 (also done lazily by renderFrame)
+ *   crhostUniqueId  rank 0 of a multi-process job makes the 128-byte id the launcher distributes
+ *   joinRanks       every process of the job: I am `rank` of `world`, rendering on CUDA device `device` */
+int prepareGpus(struct renderer *r);
+int crhostUniqueId(void *id128);
+int joinRanks(struct renderer *r, const void *id128, int rank, int world, int device);
+
+/* accessors for FFI hosts (no struct mirroring needed) */
+float *crhostRenderBuffer(struct renderer *r);
+double crhostRenderSeconds(const struct renderer *r);
+unsigned long long crhostTotalRays(const struct renderer *r);
+void crhostConfigure(struct renderer *r, int gpus, unsigned tileWidth, unsigned tileHeight, int quiet);
+void crhostImageSize(const struct renderer *r, unsigned *w, unsigned *h, int *samples, int *bounces);
+void *crhostComm(struct renderer *r);
+const void *crhostPrepared(struct renderer *r);
+int crhostTileCount(const struct renderer *r);
+void crhostSetRank(struct renderer *r, int rank, int world);
+void crhostResetQueue(struct renderer *r);
+int takeRankTiles(struct renderer *r, int *rects, int *nums);
 
 /* worker entry point with the signature of renderThread (void *(*)(void *)) */
 void *gpuRenderThread(void *arg);

@@ -5,7 +5,7 @@
  * src/renderer/renderer.c:40-180) starts worker threads through a `struct crThread` slot whose
  * `threadFunc` is today `renderThread` (renderer.c:258-327) or `networkRenderThread`
  * (src/utils/protocol/server.c:215-263).  A GPU worker thread occupies the same slot
- * (c-ray_b200/host/gpu_render_thread.c, binding shown in INTEGRATION.md) and calls ONLY the functions
+ * (c-ray_b200/host/cr_renderer.c `gpuRenderThread`, reference-side binding in INTEGRATION.md) and calls ONLY the functions
  * below — plain pointers and sizes, no CUDA or torch types.
  *
  *   reference interface replaced                                  entry point here
@@ -68,6 +68,26 @@ const char *crgpu_last_error(void);
  * the layout of state.renderBuffer, scene.c:200 + texture.c:24-28), zero-initialised. */
 int crgpu_scene_create(const struct crs_scene *flat, int device, crgpu_scene **out);
 int crgpu_scene_destroy(crgpu_scene *s);
+
+/* The two halves of crgpu_scene_create, for hosts that render many frames of one scene or one frame on several GPUs (the
+ * reference rebuilds nothing between frames either: loadScene builds the BVHs once, scene.c:111-213).  crgpu_prepare
+ * validates the flat scene and re-lays it out for the kernels into ONE pinned host slab (device-independent, host threads);
+ * crgpu_scene_create_prepared is then a single host->device copy.  Image size / sample count / bounces / camera are taken
+ * from the flat scene at prepare time; crgpu_prepared_update_config re-reads them (after crscene_set_config) without
+ * repacking.  crgpu_prepared_slab exposes the slab bytes (what crosses PCIe per frame; tests pin their checksum). */
+typedef struct crgpu_prepared crgpu_prepared;
+int  crgpu_prepare(const struct crs_scene *flat, crgpu_prepared **out);
+int  crgpu_prepared_update_config(crgpu_prepared *p, const struct crs_scene *flat);
+int  crgpu_prepared_slab(const crgpu_prepared *p, const void **slab, size_t *bytes);
+void crgpu_prepared_free(crgpu_prepared *p);
+int  crgpu_scene_create_prepared(const crgpu_prepared *p, int device, crgpu_scene **out);
+
+/* Device memory released by crgpu_scene_destroy is kept in a per-device cache for the next scene (a frame's 35 GB of
+ * wavefront state costs 10-55 ms to cudaMalloc and 0.3-0.5 s to cudaFree); crgpu_device_trim returns it to the driver. */
+int crgpu_device_trim(int device);
+/* Page-locked host memory for buffers that cross PCIe every frame (renderBuffer, scene.c:200); NULL on failure. */
+void *crgpu_host_alloc(size_t bytes);
+void  crgpu_host_free(void *p);
 
 /* Limit on paths in flight per wavefront batch (default: what fits in 40% of the free device memory at
  * 137 B per path, at most 256M); a tile's passes are processed in batches of floor(max_paths / tile_pixels)

@@ -23,6 +23,8 @@ cudaError_t cudaGetLastError(void) { return 0; }
 const char *cudaGetErrorString(cudaError_t e) { (void)e; return "stub"; }
 cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 cudaError_t cudaFree(void *p) { free(p); return 0; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned f) { (void)f; *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int k) { (void)k; note("memcpy",s,n); memcpy(d, s, n); t_last=now_(); return 0; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int k, cudaStream_t st) { (void)k; (void)st; memcpy(d, s, n); return 0; }
 cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, int k, cudaStream_t st) { (void)k; (void)st; for (size_t y = 0; y < h; ++y) memcpy((char *)d + y * dp, (const char *)s + y * sp, w); return 0; }

@@ -31,12 +31,14 @@ def test_nccl_library_exports_every_declared_symbol():
     import subprocess
     import sys
     names = declared_symbols("crgpu_nccl.h")
-    assert names == ["crgpu_comm_create", "crgpu_comm_destroy", "crgpu_comm_gather_tiles"]
+    assert names == ["crgpu_comm_create", "crgpu_comm_create_rank", "crgpu_comm_destroy", "crgpu_comm_gather_tiles",
+                     "crgpu_comm_gather_tiles_rank", "crgpu_comm_set_stream", "crgpu_comm_unique_id"]
     code = ("import ctypes as C, sys\n"
             "C.CDLL(sys.argv[1] + '/libcrgpu.so', mode=C.RTLD_GLOBAL)\n"
             "L = C.CDLL(sys.argv[1] + '/libcrgpu_nccl.so')\n"
             "[getattr(L, n) for n in sys.argv[2:]]\n"
             "assert L.crgpu_comm_create(None, 0, None) != 0\n"      # bad arguments are rejected before any NCCL call
+            "assert L.crgpu_comm_create_rank(None, 0, 1, 0, None) != 0 and L.crgpu_comm_unique_id(None) != 0\n"
             "print('NCCL-ABI-OK')\n")
     r = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "c-ray_b200")] + names, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=120)

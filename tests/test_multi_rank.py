@@ -1,6 +1,7 @@
-"""CPU test of the N>1 path: world_size-2 gloo processes shard the tile grid, "render" their tiles with the
-CPU oracle (test infrastructure standing in for the GPU), and the SAME gather code bench.py uses on NCCL
-(c-ray_b200/shard.py) must reassemble a frame bit-identical to a single-rank render."""
+"""CPU test of the N>1 path: world_size-2 gloo processes take their share of the tile queue from the host C dispatcher
+(libcrhost.so takeRankTiles — the code a torchrun rank of bench.py runs), "render" those tiles with the CPU oracle (test
+infrastructure standing in for the GPU) and gather the packed tiles on rank 0 (gloo here, the C NCCL gather on GPUs): the
+frame must be bit-identical to a single-rank render, and the ranks' shares must partition the tile queue."""
 import os
 import socket
 import subprocess
@@ -14,17 +15,28 @@ WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.join(sys.argv[1], "c-ray_b200")); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
-import shard, oracle_lib as O
+import shard, crhost, oracle_lib as O
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 sc = O.OracleScene(sys.argv[2])
-W, H, tile = sc.W, sc.H, 16
+W, H = sc.W, sc.H
+R = crhost.Renderer(sys.argv[2], tile=16)                      # the C dispatcher: tile grid, order, rank assignment
+mine, owner, every = R.rank_tiles(rank, world)
+assert len(every) == len(owner) and sorted(map(tuple, mine.tolist())) == sorted(tuple(every[k]) for k in range(len(every)) if owner[k] == rank)
 fb = np.zeros((H, W, 3), dtype=np.float32)
-for r in shard.rank_rects(W, H, tile, rank, world):
-    sc.render(threads=1, tile=r, rgb=fb)
+for r in mine:
+    sc.render(threads=1, tile=tuple(int(v) for v in r), rgb=fb)
 t = torch.from_numpy(fb)
-shard.gather_to_rank0(t, W, H, tile, rank, world, dist)
+share = [[tuple(int(v) for v in every[k]) for k in range(len(every)) if owner[k] == q] for q in range(world)]
+pad = max(sum((x1 - x0) * (y1 - y0) * 3 for x0, y0, x1, y1 in s) for s in share)
+buf = torch.zeros(pad)
+p = shard.pack(t, share[rank])
+buf[:p.numel()] = p
+outs = [torch.empty(pad) for _ in range(world)] if rank == 0 else None
+dist.gather(buf, outs, dst=0)
 if rank == 0:
+    for q in range(1, world):
+        shard.unpack_into(t, share[q], outs[q])
     t.numpy().tofile(sys.argv[3])
 dist.barrier()
 dist.destroy_process_group()
