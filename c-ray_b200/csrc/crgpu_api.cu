@@ -361,7 +361,8 @@ static int alloc_wave(crgpu_scene *s, uint64_t paths) {
 	w.hit = (float4 *)take(n * 16); w.L = (float4 *)take(n * 16);
 	w.hitInst = (int *)take(n * 4); w.perm = (unsigned *)take(n * 4);
 	w.hitKey = (unsigned char *)take(n);
-	take(n * 16);                                                  /* spare 16-B lane (keeps the block size a round 137 -> 153 B/path) */
+	w.perm2 = (unsigned *)take(n * 4); w.dirKey = (unsigned char *)take(n);
+	take(n * 11);                                                  /* spare 16-B lane (keeps the block size a round 137 -> 153 B/path) */
 	s->cap_paths = paths;
 	return CRGPU_OK;
 }
@@ -738,12 +739,12 @@ extern "C" int crgpu_scene_create_prepared(const crgpu_prepared *p, int device, 
 	s->fb_floats = (size_t)d.image_width * d.image_height * 3u;
 	{ void *q = nullptr; FAIL_IF(ctx_alloc(device, s->fb_floats * sizeof(float), &q)); s->fb = static_cast<float *>(q); }
 	CUS(cudaMemsetAsync(s->fb, 0, s->fb_floats * sizeof(float), s->stream));
-	s->small_bytes = 512 * sizeof(unsigned) + 256 + 80 * sizeof(unsigned long long);
+	s->small_bytes = 1024 * sizeof(unsigned) + 256 + 80 * sizeof(unsigned long long);
 	FAIL_IF(ctx_alloc(device, s->small_bytes, &s->small));
 	CUS(cudaMemsetAsync(s->small, 0, s->small_bytes, s->stream));
 	s->wb.hist = static_cast<unsigned *>(s->small);
-	s->wb.counts = s->wb.hist + 512;
-	s->wb.stats = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(s->small) + 512 * sizeof(unsigned) + 256);
+	s->wb.counts = s->wb.hist + 1024;
+	s->wb.stats = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(s->small) + 1024 * sizeof(unsigned) + 256);
 	{
 		/* Paths in flight per wavefront batch.  Every batch pays a fixed ~7 ms (the serial chain of its bounces: each
 		 * late bounce lasts as long as its slowest ray), so batches should be as large as memory allows:
@@ -833,6 +834,7 @@ static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, in
 	const bool timing = (flags & CRGPU_FLAG_TIME_KERNELS) != 0;
 	const int maxDepth = (int)s->dev.bounces;
 	const int grid = s->sm_count * 8;
+	const int dirmode = crg_dir_mode();
 	uint64_t launches = 0;
 	float trace_ms = 0.f, shade_ms = 0.f;
 	if (timing) CU(cudaEventRecord(s->ev[0], st));
@@ -850,12 +852,14 @@ static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, in
 		for (int depth = 0; depth < maxDepth; ++depth) {
 			if (depth >= CRG_TAIL_FROM && !count) { crg_launch_tail(s->dev_copy, s->wb, cur, depth, maxDepth, st); ++launches; }
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
-			crg_launch_trace(s->dev, s->wb, cur, count, grid, st);
+			crg_launch_trace(s->dev, s->wb, cur, count, dirmode != 0 && depth > 0, grid, st);
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
 			crg_launch_bucket(s->wb, cur, grid, st);
-			crg_launch_shade(s->dev_copy, s->wb, cur, depth, maxDepth, grid, st);
+			const bool sort_next = dirmode != 0 && depth + 1 < maxDepth;
+			crg_launch_shade(s->dev_copy, s->wb, cur, depth, maxDepth, sort_next ? dirmode : 0, grid, st);
+			if (sort_next) { crg_launch_dirsort(s->wb, cur ^ 1, grid, st); ++launches; }    /* K4b: the next bounce's rays by direction bin */
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
-			launches += 3;
+			launches += 2 + (uint64_t)crg_shade_launches_per_bounce();
 			cur ^= 1;
 		}
 		crg_launch_accumulate(s->fb, s->wb.L, td, (int)s->dev.image_width, (int)s->dev.image_height, grid, st); ++launches;
@@ -909,26 +913,31 @@ extern "C" int crgpu_render_tiles(crgpu_scene *s, const int *rects, int nrects, 
 	}
 	std::vector<int> key(rects, rects + 4 * (size_t)nrects);
 	if (key != s->pixel_key) {                         /* rebuild the pixel list only when the tile set changes */
-		std::vector<uint32_t> px;
-		px.reserve((size_t)total);
-		for (int i = 0; i < nrects; ++i)
-			for (int y = rects[4 * i + 1]; y < rects[4 * i + 3]; ++y)
-				for (int x = rects[4 * i]; x < rects[4 * i + 2]; ++x) px.push_back((uint32_t)x | ((uint32_t)y << 16));
-		CU(cudaStreamSynchronize(s->stream));
-		if (s->pixel_cap < px.size()) {
+		if (total > 0xffffffffull) return fail(CRGPU_ERR_UNSUPPORTED, "tile set of more than 2^32 pixels");
+		/* the list is expanded ON THE DEVICE from the rectangles (a 1080p frame is 2 M entries, an 8K frame 33 M: building and
+		 * uploading them from the host cost ~10 ms per frame): upload 16 B + 4 B per tile, one kernel writes x | y << 16 */
+		std::vector<unsigned> offs((size_t)nrects);
+		unsigned acc = 0u;
+		for (int i = 0; i < nrects; ++i) { offs[(size_t)i] = acc; acc += (unsigned)((rects[4 * i + 2] - rects[4 * i]) * (rects[4 * i + 3] - rects[4 * i + 1])); }
+		const size_t need = (size_t)total * sizeof(uint32_t) + (size_t)nrects * 20u + 256u;
+		if (s->pixel_cap * sizeof(uint32_t) < need) {
+			CU(cudaStreamSynchronize(s->stream));       /* the previous list may still be in use by queued kernels */
 			ctx_free(s->device, s->pixels, s->pixel_cap * sizeof(uint32_t));
 			s->pixels = nullptr; s->pixel_cap = 0;
 			void *q = nullptr;
-			int arc = ctx_alloc(s->device, px.size() * sizeof(uint32_t), &q);
+			int arc = ctx_alloc(s->device, need, &q);
 			if (arc) return arc;
 			s->pixels = static_cast<uint32_t *>(q);
-			s->pixel_cap = px.size();
+			s->pixel_cap = (need + 3u) / 4u;
 		}
-		/* on the scene's own stream, then wait: a plain cudaMemcpy from pageable memory runs on the legacy stream and may
-		 * return while the last DMA chunk is still in flight; kernels on a NON-BLOCKING stream are not ordered after it,
-		 * so the first k_generate of this tile set could read the previous set's coordinates */
-		CU(cudaMemcpyAsync(s->pixels, px.data(), px.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
-		CU(cudaStreamSynchronize(s->stream));
+		/* rectangle table behind the pixel list (same block); both copies are from pageable memory, i.e. staged before the call
+		 * returns, and ordered before the kernel on the scene's stream */
+		uint8_t *tab = reinterpret_cast<uint8_t *>(s->pixels) + (((size_t)total * sizeof(uint32_t) + 255u) & ~(size_t)255u);
+		CU(cudaMemcpyAsync(tab, rects, (size_t)nrects * 16u, cudaMemcpyHostToDevice, s->stream));
+		CU(cudaMemcpyAsync(tab + (size_t)nrects * 16u, offs.data(), (size_t)nrects * 4u, cudaMemcpyHostToDevice, s->stream));
+		CU(cudaStreamSynchronize(s->stream));           /* offs is a local; costs ~20 us, once per tile set */
+		crg_launch_pixel_list(s->pixels, reinterpret_cast<const int4 *>(tab), reinterpret_cast<const unsigned *>(tab + (size_t)nrects * 16u), nrects, s->stream);
+		CU(cudaGetLastError());
 		s->pixel_key.swap(key);
 	}
 	TileDesc td;

@@ -13,14 +13,24 @@
  * with ONE global atomicAdd (cursor = wb.hist[256+k]).  Output: perm[bucket_base + rank] = live index.
  * Order inside a bucket is arbitrary; results do not depend on it (every path carries its own RNG + id). */
 #define CRG_BUCKET_ITEMS 8
+/* DIR = false: K4 (keys = hitKey, sizes hist[0..255], cursors hist[256..511], output perm).
+ * DIR = true:  K4b, the same counting sort over the NEXT bounce's rays by direction bin (keys = dirKey written by K3, sizes
+ *              hist[512..767], cursors hist[768..1023], output perm2): K2 hands rays to its lanes in perm2 order, so the 32 rays
+ *              of a warp point into the same octant and walk the BVH in the same child order — fewer divergent steps. */
+template <bool DIR>
 __global__ void __launch_bounds__(256) k_bucket(WaveBuffers wb, int cur) {
 	__shared__ unsigned s_base[256], s_cnt[256], s_off[256];
 	const unsigned n = wb.counts[cur];
 	const unsigned t = threadIdx.x;
-	s_cnt[t] = wb.hist[t];
+	unsigned *__restrict__ sizes = wb.hist + (DIR ? 512 : 0);
+	unsigned *__restrict__ cursors = wb.hist + (DIR ? 768 : 256);
+	const unsigned char *__restrict__ keys = DIR ? wb.dirKey : wb.hitKey;
+	unsigned *__restrict__ out = DIR ? wb.perm2 : wb.perm;
+	s_cnt[t] = sizes[t];
 	__syncthreads();
 	if (t == 0u) { unsigned acc = 0u; for (int k = 0; k < 256; ++k) { s_base[k] = acc; acc += s_cnt[k]; } }
 	__syncthreads();
+	if (!DIR && blockIdx.x == 0u && t == 0u) wb.counts[4] = s_base[1];      /* = bucket 0's size: perm[0 .. counts[4]) are the misses (K3 split) */
 	const unsigned chunk = 256u * CRG_BUCKET_ITEMS;
 	for (unsigned c0 = blockIdx.x * chunk; c0 < n; c0 += gridDim.x * chunk) {
 		s_cnt[t] = 0u;
@@ -30,15 +40,15 @@ __global__ void __launch_bounds__(256) k_bucket(WaveBuffers wb, int cur) {
 		for (int k = 0; k < CRG_BUCKET_ITEMS; ++k) {
 			const unsigned i = c0 + (unsigned)k * 256u + t;
 			key[k] = 0xffffffffu;
-			if (i < n) { key[k] = wb.hitKey[i]; rank[k] = atomicAdd(&s_cnt[key[k]], 1u); }
+			if (i < n) { key[k] = keys[i]; rank[k] = atomicAdd(&s_cnt[key[k]], 1u); }
 		}
 		__syncthreads();
-		s_off[t] = s_cnt[t] ? atomicAdd(&wb.hist[256u + t], s_cnt[t]) : 0u;
+		s_off[t] = s_cnt[t] ? atomicAdd(&cursors[t], s_cnt[t]) : 0u;
 		__syncthreads();
 #pragma unroll
 		for (int k = 0; k < CRG_BUCKET_ITEMS; ++k) {
 			const unsigned i = c0 + (unsigned)k * 256u + t;
-			if (key[k] != 0xffffffffu) wb.perm[s_base[key[k]] + s_off[key[k]] + rank[k]] = i;
+			if (key[k] != 0xffffffffu) out[s_base[key[k]] + s_off[key[k]] + rank[k]] = i;
 		}
 		__syncthreads();
 	}
@@ -63,9 +73,10 @@ CRD void cr_finish_path(float4 *__restrict__ Lbuf, unsigned id) {
 }
 
 /* returns true when the path continues with (p_next, d_next) and the updated weight / rng / id */
+template <bool MAYBE_MISS = true>
 CRD bool cr_shade_one(const DevScene &sc, float4 *__restrict__ Lbuf, v3 o, v3 d, const Hit &hit, float &wr, float &wg, float &wbl,
 					  unsigned &id, uint64_t &rng, int depth, int maxDepth, v3 &p_next, v3 &d_next) {
-	if (hit.inst < 0) {                                                               /* pathtrace.c:39-42 */
+	if (MAYBE_MISS && hit.inst < 0) {                                                               /* pathtrace.c:39-42 */
 		const col4 bg = cr_sample_background(sc, d);
 		cr_add_radiance(Lbuf, id, wr * bg.r, wg * bg.g, wbl * bg.b);
 		return false;
@@ -94,19 +105,51 @@ CRD bool cr_shade_one(const DevScene &sc, float4 *__restrict__ Lbuf, v3 o, v3 d,
 	return false;
 }
 
-/* ---- K3 (+ compaction) ---------------------------------------------------------------------------------------------- */
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth) {
+/* direction bin of a ray for K4b: sign octant (bvh.c:370-372 picks the near/far planes from exactly these bits), optionally
+ * times the major axis.  Any binning is legal: the order rays are traced in never changes a result. */
+CRD unsigned cr_dir_bin(v3 d, int mode) {
+	unsigned key = (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
+	if (mode >= 2) {
+		const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+		const unsigned major = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
+		key |= major << 3;                       /* 0..23 */
+	}
+	return key;
+}
+
+/* ---- K3 (+ compaction) ----------------------------------------------------------------------------------------------
+ * PART 0: every ray of the queue.  PART 1 / 2: the two halves of a split launch — 1 = the misses (bucket 0 = perm[0 .. counts[4]):
+ * background lookup + radiance, the path always ends, nothing to compact), 2 = the hits (perm[counts[4] .. n)).  The miss half
+ * needs a third of the registers of the hit half, so it runs at twice the occupancy; on hdr.json 40% of all rays are misses. */
+template <int MINB, int PART>
+__global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth, int dirmode) {
 	const DevScene &sc = *scp;
 	const unsigned n = wb.counts[cur];
 	const int nxt = cur ^ 1;
+	const unsigned stride = gridDim.x * blockDim.x;
+	if (PART == 1) {
+		const unsigned n0 = wb.counts[4];
+		for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n0; j += stride) {
+			const unsigned i = wb.perm[j];
+			const float4 a = wb.stA[cur][i];
+			const float4 b = wb.stB[cur][i];
+			const uint4 c = wb.stC[cur][i];
+			unsigned id = c.y;
+			const col4 bg = cr_sample_background(sc, v3make(a.w, b.x, b.y));                 /* pathtrace.c:39-42 */
+			cr_add_radiance(wb.L, id, b.z * bg.r, b.w * bg.g, __uint_as_float(c.x) * bg.b);
+		}
+		return;
+	}
+	__shared__ unsigned s_dir[32];                                /* direction-bin sizes of the rays this block writes */
+	if (threadIdx.x < 32) s_dir[threadIdx.x] = 0u;
+	__syncthreads();
 	if (blockIdx.x == 0 && threadIdx.x == 0) wb.counts[2] = 0u;   /* K2's work counter, for the next bounce */
 	if (blockIdx.x == 0) { wb.hist[threadIdx.x] = 0u; wb.hist[256 + threadIdx.x] = 0u; }   /* K2/K4 histogram + cursors (blockDim.x == 256) */
 	const unsigned lane = threadIdx.x & 31u;
 	/* whole warps iterate together so the ballot below is convergent */
-	const unsigned stride = gridDim.x * blockDim.x;
-	const unsigned nround = (n + 31u) & ~31u;
-	for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += stride) {
+	const unsigned first = PART == 2 ? wb.counts[4] : 0u;
+	const unsigned nround = first + ((n - first + 31u) & ~31u);
+	for (unsigned j = first + blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += stride) {
 		bool alive = false;
 		v3 p_next = v3make(0, 0, 0), d_next = v3make(0, 0, 0);
 		float wr = 0.f, wg = 0.f, wbl = 0.f;
@@ -124,7 +167,7 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 			wr = b.z; wg = b.w; wbl = __uint_as_float(c.x);
 			id = c.y;
 			rng = (uint64_t)c.z | ((uint64_t)c.w << 32);
-			alive = cr_shade_one(sc, wb.L, v3make(a.x, a.y, a.z), v3make(a.w, b.x, b.y), hit, wr, wg, wbl, id, rng, depth, maxDepth, p_next, d_next);
+			alive = cr_shade_one<PART != 2>(sc, wb.L, v3make(a.x, a.y, a.z), v3make(a.w, b.x, b.y), hit, wr, wg, wbl, id, rng, depth, maxDepth, p_next, d_next);
 		}
 		/* order-preserving warp compaction, one atomic per warp */
 		const unsigned mask = __ballot_sync(0xffffffffu, alive);
@@ -137,8 +180,17 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 				wb.stA[nxt][k] = make_float4(p_next.x, p_next.y, p_next.z, d_next.x);
 				wb.stB[nxt][k] = make_float4(d_next.y, d_next.z, wr, wg);
 				wb.stC[nxt][k] = make_uint4(__float_as_uint(wbl), id, (unsigned)(rng & 0xffffffffull), (unsigned)(rng >> 32));
+				if (dirmode) {
+					const unsigned key = cr_dir_bin(d_next, dirmode);
+					wb.dirKey[k] = (unsigned char)key;
+					atomicAdd(&s_dir[key], 1u);
+				}
 			}
 		}
+	}
+	if (dirmode) {
+		__syncthreads();
+		if (threadIdx.x < 32 && s_dir[threadIdx.x]) atomicAdd(&wb.hist[512 + threadIdx.x], s_dir[threadIdx.x]);
 	}
 }
 
@@ -260,18 +312,35 @@ __global__ void k_kat(const DevScene *__restrict__ scp, const int32_t *__restric
 }
 
 void crg_launch_bucket(const WaveBuffers &wb, int cur, int grid, cudaStream_t st) {
-	k_bucket<<<grid, 256, 0, st>>>(wb, cur);
+	k_bucket<false><<<grid, 256, 0, st>>>(wb, cur);
 }
 void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, cudaStream_t st) {
 	k_tail<<<128, 128, 0, st>>>(dsc, wb, cur, depth, maxDepth);
 }
-void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int grid, cudaStream_t st) {
-	static int minb = 0;
-	if (!minb) { const char *e = getenv("CRGPU_SHADE_MINB"); minb = e ? atoi(e) : 2; }
-	if (minb == 3) k_shade<3><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
-	else if (minb == 4) k_shade<4><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
-	else k_shade<2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth);
+/* CRGPU_SHADE_MINB = 2|3|4 (blocks per SM of the hit/all kernel: 128 / 80 / 64 registers), CRGPU_SHADE_SPLIT = 0|1 (separate
+ * miss kernel at 4 blocks per SM) — read once; the defaults are what measured best on hdr.json / venus.json (profiles/) */
+void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int dirmode, int grid, cudaStream_t st) {
+	static const int minb = [] { const char *e = getenv("CRGPU_SHADE_MINB"); const int v = e ? atoi(e) : 2; return v >= 2 && v <= 4 ? v : 2; }();
+	static const int split = [] { const char *e = getenv("CRGPU_SHADE_SPLIT"); return e ? atoi(e) : 1; }();
+	if (split) {
+		k_shade<4, 1><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
+		if (minb == 3) k_shade<3, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
+		else if (minb == 4) k_shade<4, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
+		else k_shade<2, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
+		return;
+	}
+	if (minb == 3) k_shade<3, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
+	else if (minb == 4) k_shade<4, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
+	else k_shade<2, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
 }
+void crg_launch_dirsort(const WaveBuffers &wb, int nxt, int grid, cudaStream_t st) {
+	k_bucket<true><<<grid, 256, 0, st>>>(wb, nxt);
+}
+int crg_dir_mode(void) {
+	static const int mode = [] { const char *e = getenv("CRGPU_TRACE_SORT"); const int v = e ? atoi(e) : 1; return v >= 0 && v <= 2 ? v : 1; }();
+	return mode;
+}
+int crg_shade_launches_per_bounce(void) { const char *e = getenv("CRGPU_SHADE_SPLIT"); return (e ? atoi(e) : 1) ? 2 : 1; }
 void crg_launch_accumulate(float *fb, const float4 *L, const TileDesc &td, int W, int H, int grid, cudaStream_t st) {
 	k_accumulate<<<grid, 256, 0, st>>>(fb, L, td, W, H);
 }

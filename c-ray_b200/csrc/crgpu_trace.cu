@@ -8,6 +8,23 @@
 #include "crgpu_trace.cuh"
 #include <cstdlib>
 
+/* ---- pixel list of a tile set: blockIdx.y = tile, the block's threads walk its pixels row by row (crgpu_render_tiles) ---------------- */
+__global__ void __launch_bounds__(256) k_pixel_list(uint32_t *__restrict__ pixels, const int4 *__restrict__ rects, const unsigned *__restrict__ offs) {
+	const int4 r = rects[blockIdx.y];
+	const unsigned w = (unsigned)(r.z - r.x), n = w * (unsigned)(r.w - r.y);
+	uint32_t *out = pixels + offs[blockIdx.y];
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const unsigned y = i / w, x = i - y * w;
+		out[i] = (uint32_t)(r.x + (int)x) | ((uint32_t)(r.y + (int)y) << 16);
+	}
+}
+void crg_launch_pixel_list(uint32_t *pixels, const int4 *rects, const unsigned *offs, int nrects, cudaStream_t st) {
+	for (int first = 0; first < nrects; first += 32768) {            /* gridDim.y <= 65535 */
+		const int cnt = nrects - first < 32768 ? nrects - first : 32768;
+		k_pixel_list<<<dim3(4, (unsigned)cnt), 256, 0, st>>>(pixels, rects + first, offs + first);
+	}
+}
+
 /* ---- K1 ------------------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, TileDesc td) {
 	const unsigned tile_pixels = td.npix;
@@ -25,7 +42,7 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
 		wb.stC[0][id] = make_uint4(__float_as_uint(1.0f), id, (unsigned)(rng & 0xffffffffull), (unsigned)(rng >> 32));
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counts[0] = n; wb.counts[1] = 0u; wb.counts[2] = 0u; wb.counts[3] = 0u; }
-	if (blockIdx.x == 0) { wb.hist[threadIdx.x] = 0u; wb.hist[256 + threadIdx.x] = 0u; }   /* blockDim.x == 256 */
+	if (blockIdx.x == 0) { for (int k = 0; k < 4; ++k) wb.hist[k * 256 + threadIdx.x] = 0u; }   /* blockDim.x == 256 */
 }
 
 /* ---- K2: persistent warps with dynamic ray refill ----------------------------------------------------------------------
@@ -39,8 +56,8 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
 #define CRG_STAGE_MIN_RAYS 65536u
 #define CRG_MAX_STEPS 8000000u   /* > 30x the node count of any scene that fits the 2^23-node address space we support */
 
-template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb, int cur, int refill, int burst) {
+template <bool COUNT, int MINB, bool DEFER>
+__global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb, int cur, int refill, int burst, int sorted) {
 	const unsigned n = wb.counts[cur];
 	const unsigned lane = threadIdx.x & 31u;
 	const float4 *__restrict__ stA = wb.stA[cur];
@@ -48,6 +65,9 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 	TraceCounters tc = { 0u, 0u, 0u, 0u };
 	__shared__ unsigned s_hist[256];
 	s_hist[threadIdx.x] = 0u;            /* blockDim.x == 256 */
+	/* K3 + K4b of the previous bounce are done with the direction-bin counters: clear them for this bounce's K3 */
+	if (blockIdx.x == 0) { wb.hist[512 + threadIdx.x] = 0u; wb.hist[768 + threadIdx.x] = 0u; }
+	const unsigned *__restrict__ order = sorted ? wb.perm2 : nullptr;     /* rays in direction-bin order (see k_dirsort) */
 	__syncthreads();
 	/* ---- stage the top-of-tree pair nodes into shared memory: one TMA bulk copy (cp.async.bulk, SASS UBLKCP) per
 	 *      block, completion signalled on an mbarrier; skipped for the small tail launches where it cannot pay off */
@@ -93,8 +113,9 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 			if (lane == 0u) base = atomicAdd(&wb.counts[2], nidle);
 			base = __shfl_sync(0xffffffffu, base, 0);
 			if (base + nidle >= n) exhausted = true;
-			const unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
-			if (!busy && i < n) {
+			const unsigned slot = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+			if (!busy && slot < n) {
+				const unsigned i = order ? order[slot] : slot;
 				const float4 a = stA[i];
 				const float4 b = stB[i];
 				ray = i;
@@ -112,8 +133,10 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 		for (int k = 0; k < burst; ++k) {
 			const bool wn = busy && tr.wants_node();
 			if (!__any_sync(0xffffffffu, wn)) break;
-			if (wn) { tr.node_step(sc, &tc); ++steps; }
+			if (wn) { tr.template node_step<DEFER>(sc, &tc); ++steps; }
 		}
+		/* Phase T (DEFER): the triangles of every lane that reached a leaf during the burst, together */
+		if (DEFER && busy && tr.wants_leaf()) tr.leaf_step(sc, &tc);
 		/* Phase I: one pending instance (ray transform + sphere test, or entry into a mesh BVH) */
 		if (busy && tr.wants_instance()) { tr.instance_step(sc, &tc); ++steps; }
 		/* Phase W: write back finished rays */
@@ -160,9 +183,11 @@ void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDe
 /* K2 is persistent: the grid is exactly the number of blocks the device can keep resident.  MINB (blocks per SM
  * the compiler must make room for: 2 -> <=128 registers, 3 -> <=80, 4 -> <=64) trades registers for latency-hiding warps;
  * CRGPU_TRACE_MINB=2|3 overrides the default for experiments. */
+#ifndef CRG_MAX_DEVICES
 #define CRG_MAX_DEVICES 64
-template <bool COUNT, int MINB>
-static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int cur, cudaStream_t st) {
+#endif
+template <bool COUNT, int MINB, bool DEFER>
+static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int cur, bool sorted, cudaStream_t st) {
 	/* launch shape per DEVICE: the host mirror drives several GPUs from one process (one thread each), and both the
 	 * occupancy answer and the opt-in shared-memory attribute belong to a device, not to the process */
 	struct Shape { int grid; size_t smem; };
@@ -178,25 +203,30 @@ static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int 
 		if (!sh.grid || sh.smem != smem) {
 			int sms = 0, occ = 0;
 			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-			cudaFuncSetAttribute(k_trace<COUNT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, CRG_STAGE_PAIRS * (int)sizeof(PairNode));
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<COUNT, MINB>, 256, smem);
+			cudaFuncSetAttribute(k_trace<COUNT, MINB, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, CRG_STAGE_PAIRS * (int)sizeof(PairNode));
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<COUNT, MINB, DEFER>, 256, smem);
 			sh.grid = sms * (occ > 0 ? occ : 1);
 			sh.smem = smem;
 		}
 		grid = sh.grid;
 	}
-	static int refill = 0, burst = 0;
-	if (!refill) { const char *e = getenv("CRGPU_TRACE_REFILL"); refill = e ? atoi(e) : CRG_REFILL; if (refill < 1 || refill > 32) refill = CRG_REFILL;
-		e = getenv("CRGPU_TRACE_BURST"); burst = e ? atoi(e) : CRG_NODE_BURST; if (burst < 1) burst = CRG_NODE_BURST; }
-	k_trace<COUNT, MINB><<<grid, 256, smem, st>>>(sc, wb, cur, refill, burst);
+	static const int refill = [] { const char *e = getenv("CRGPU_TRACE_REFILL"); const int v = e ? atoi(e) : CRG_REFILL; return v >= 1 && v <= 32 ? v : CRG_REFILL; }();
+	static const int burst = [] { const char *e = getenv("CRGPU_TRACE_BURST"); const int v = e ? atoi(e) : (DEFER ? 4 : CRG_NODE_BURST); return v >= 1 ? v : CRG_NODE_BURST; }();
+	k_trace<COUNT, MINB, DEFER><<<grid, 256, smem, st>>>(sc, wb, cur, refill, burst, sorted ? 1 : 0);
 }
 
-void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, int grid, cudaStream_t st) {
+void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, bool sorted, int grid, cudaStream_t st) {
 	(void)grid;
-	static int minb = 0;
-	if (!minb) { const char *e = getenv("CRGPU_TRACE_MINB"); minb = e ? atoi(e) : 3; if (minb < 2 || minb > 4) minb = 3; }
-	if (count) { launch_trace_variant<true, 3>(sc, wb, cur, st); return; }
-	if (minb == 4) launch_trace_variant<false, 4>(sc, wb, cur, st);
-	else if (minb == 2) launch_trace_variant<false, 2>(sc, wb, cur, st);
-	else launch_trace_variant<false, 3>(sc, wb, cur, st);
+	static const int minb = [] { const char *e = getenv("CRGPU_TRACE_MINB"); const int v = e ? atoi(e) : 3; return v >= 2 && v <= 4 ? v : 3; }();
+	static const int defer = [] { const char *e = getenv("CRGPU_TRACE_DEFER"); return e ? atoi(e) : 1; }();
+	if (count) { if (defer) launch_trace_variant<true, 3, true>(sc, wb, cur, sorted, st); else launch_trace_variant<true, 3, false>(sc, wb, cur, sorted, st); return; }
+	if (defer) {
+		if (minb == 4) launch_trace_variant<false, 4, true>(sc, wb, cur, sorted, st);
+		else if (minb == 2) launch_trace_variant<false, 2, true>(sc, wb, cur, sorted, st);
+		else launch_trace_variant<false, 3, true>(sc, wb, cur, sorted, st);
+	} else {
+		if (minb == 4) launch_trace_variant<false, 4, false>(sc, wb, cur, sorted, st);
+		else if (minb == 2) launch_trace_variant<false, 2, false>(sc, wb, cur, sorted, st);
+		else launch_trace_variant<false, 3, false>(sc, wb, cur, sorted, st);
+	}
 }

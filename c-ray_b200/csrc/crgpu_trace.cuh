@@ -232,11 +232,12 @@ struct Traversal {
 	const PackedTri *__restrict__ tris;
 	uint32_t slotBase, node, topNext;
 	uint32_t pendA, cntA, pendB, cntB;     /* pending top-level leaf items: A (left leaf) before B (right leaf) */
+	uint32_t leafA, leafB, leafN;          /* DEFER: bottom-level leaf triangles not yet tested — slots [leafA, +nA) then [leafB, +nB), leafN = nA | nB << 16 */
 	int sp, spBase, curInst;
 	bool bottom, instHit;
 	uint32_t *stack;       /* 2*CRG_MAX_STACK+2 entries of thread-local memory, owned by the caller (keeps the scalars in registers) */
 
-	CRD bool done() const { return !bottom && (cntA | cntB) == 0u && node == CRG_END; }
+	CRD bool done() const { return !bottom && (cntA | cntB) == 0u && node == CRG_END && leafN == 0u; }
 
 	CRD void begin(const DevScene &sc, v3 ro, v3 rd) {
 		best.t = CR_FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = 0u;
@@ -249,6 +250,7 @@ struct Traversal {
 		pendA = 0u; cntA = 0u; pendB = 0u; cntB = 0u;
 		sp = 0; spBase = 0; curInst = -1;
 		bottom = false; instHit = false;
+		leafA = 0u; leafB = 0u; leafN = 0u;
 		if (sc.top.node_count < 1) {                                               /* bvh.c:362-365 */
 			node = CRG_END;
 		} else if (sc.top.node_count == 1) {                                       /* bvh.c:382-387 */
@@ -258,7 +260,8 @@ struct Traversal {
 		}
 	}
 
-	CRD bool wants_node() const { return bottom || ((cntA | cntB) == 0u && node != CRG_END); }
+	CRD bool wants_node() const { return leafN == 0u && (bottom || ((cntA | cntB) == 0u && node != CRG_END)); }
+	CRD bool wants_leaf() const { return leafN != 0u; }
 	CRD bool wants_instance() const { return !bottom && (cntA | cntB) != 0u; }
 
 	/* one iteration of the flat loop; precondition: !done() */
@@ -267,7 +270,32 @@ struct Traversal {
 		else instance_step(sc, ctr);
 	}
 
-	/* precondition: wants_node() */
+	/* the tail of a bottom-level step: once the mesh BVH is exhausted, back to the top level (instance.c:175-184) */
+	CRD void finish_bottom(const DevScene &sc) {
+		if (node == CRG_END) {
+			if (instHit) best.inst = curInst;
+			bottom = false;
+			o = wo; d = wd;
+			rs = cr_ray_setup(o, d);
+			base = sc.pairs + sc.top.pair_offset;
+			stageBase = sc.top.stage_base; stageCount = snodes ? sc.top.stage_count : 0u;
+			node = topNext;
+			spBase = 0;
+		}
+	}
+
+	/* DEFER: the triangles of the leaf/leaves the last node step reached (left leaf, then right leaf: bvh.c:402-418).  Until this has
+	 * run the lane takes no further node step, so the visiting order and the distance every later box is culled with are exactly
+	 * those of the in-line version; only the warp's interleaving differs: lanes that reached a leaf WAIT, and all waiting lanes of
+	 * the warp test their triangles together after the node burst (profiles/: K2 warp model, policy "leaves wait"). */
+	CRD void leaf_step(const DevScene &sc, TraceCounters *ctr) {
+		instHit |= cr_leaf_tris2<COUNT>(tris, slotBase, leafA, leafN & 0xffffu, leafB, leafN >> 16, o, d, best, ctr);
+		leafN = 0u;
+		finish_bottom(sc);
+	}
+
+	/* precondition: wants_node().  DEFER = true: leaf triangles are left pending for leaf_step() */
+	template <bool DEFER = false>
 	CRD void node_step(const DevScene &sc, TraceCounters *ctr) {
 		{
 			/* ---- one child-pair step (bvh.c:391-439) */
@@ -305,17 +333,12 @@ struct Traversal {
 				 * right leaf test their triangles together */
 				const uint32_t nL = (hitL && leafL) ? (q3.z & ~CRG_LEAF_BIT) : 0u;
 				const uint32_t nR = (hitR && leafR) ? (q3.w & ~CRG_LEAF_BIT) : 0u;
-				if (nL + nR) instHit |= cr_leaf_tris2<COUNT>(tris, slotBase, q3.x, nL, q3.y, nR, o, d, best, ctr);
 				node = next;
-				if (node == CRG_END) {                                             /* back to the top level (instance.c:175-184) */
-					if (instHit) best.inst = curInst;
-					bottom = false;
-					o = wo; d = wd;
-					rs = cr_ray_setup(o, d);
-					base = sc.pairs + sc.top.pair_offset;
-					stageBase = sc.top.stage_base; stageCount = snodes ? sc.top.stage_count : 0u;
-					node = topNext;
-					spBase = 0;
+				if (DEFER && (nL + nR) != 0u && nL < 65536u && nR < 65536u) {
+					leafA = q3.x; leafB = q3.y; leafN = nL | (nR << 16);               /* tested by leaf_step(), then finish_bottom() */
+				} else {
+					if (nL + nR) instHit |= cr_leaf_tris2<COUNT>(tris, slotBase, q3.x, nL, q3.y, nR, o, d, best, ctr);
+					finish_bottom(sc);
 				}
 			} else {
 				if (hitL && leafL) { pendA = q3.x; cntA = q3.z & ~CRG_LEAF_BIT; }

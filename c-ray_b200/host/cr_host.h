@@ -84,6 +84,8 @@ struct state {                     /* renderer.h:34-55 */
 	pthread_t *threads;
 	struct renderThreadState *threadStates;
 	pthread_mutex_t tileMutex;
+	pthread_mutex_t doneMutex;     /* workers signal doneCond when they finish: renderFrame wakes up at once instead of at its next 16 ms poll */
+	pthread_cond_t doneCond;
 	double renderSeconds;
 	uint64_t totalRays;
 };

@@ -71,6 +71,8 @@ struct renderer *newRenderer(void) {                              /* renderer.c:
 	struct renderer *r = calloc(1, sizeof *r);
 	if (!r) return NULL;
 	pthread_mutex_init(&r->state.tileMutex, NULL);
+	pthread_mutex_init(&r->state.doneMutex, NULL);
+	pthread_cond_init(&r->state.doneCond, NULL);
 	r->prefs.threadCount = 1;
 	r->prefs.imgType = png;
 	r->prefs.imgFilePath = "./";
@@ -258,8 +260,11 @@ void *gpuRenderThread(void *arg) {
 		if (ranked) break;                                                        /* the rank's whole share was one trip */
 	}
 	free(rects); free(nums);
+	pthread_mutex_lock(&r->state.doneMutex);
 	ts->threadComplete = true;                                    /* renderer.c:323 */
 	ts->currentTileNum = -1;
+	pthread_cond_broadcast(&r->state.doneCond);
+	pthread_mutex_unlock(&r->state.doneMutex);
 	return NULL;
 }
 
@@ -308,7 +313,18 @@ struct texture8 *renderFrame(struct renderer *r) {
 	}
 	int pauser = 0;
 	while (r->state.isRendering) {                                /* renderer.c:122-172 */
-		sleep_ms(r->state.threadStates[0].paused ? 100 : 16);
+		{	/* renderer.c:171 sleeps 16 ms (active_msec) between polls; here a finishing worker ends the wait early */
+			struct timespec until;
+			clock_gettime(CLOCK_REALTIME, &until);
+			const long add_ns = (r->state.threadStates[0].paused ? 100L : 16L) * 1000000L;
+			until.tv_nsec += add_ns;
+			if (until.tv_nsec >= 1000000000L) { until.tv_sec += 1; until.tv_nsec -= 1000000000L; }
+			pthread_mutex_lock(&r->state.doneMutex);
+			int alldone = 1;
+			for (int t = 0; t < n; ++t) alldone &= r->state.threadStates[t].threadComplete ? 1 : 0;
+			if (!alldone) pthread_cond_timedwait(&r->state.doneCond, &r->state.doneMutex, &until);
+			pthread_mutex_unlock(&r->state.doneMutex);
+		}
 		if (!r->prefs.quiet && ++pauser >= 280 / 16) {            /* the progress line, ~4x/s (renderer.c:137-158) */
 			pauser = 0;
 			uint64_t done = 0;
@@ -376,6 +392,8 @@ void destroyRenderer(struct renderer *r) {                       /* renderer.c:3
 	free_render_buffer(r);
 	free(r->state.renderTiles); free(r->state.tileOwner); free(r->state.threads); free(r->state.threadStates);
 	pthread_mutex_destroy(&r->state.tileMutex);
+	pthread_mutex_destroy(&r->state.doneMutex);
+	pthread_cond_destroy(&r->state.doneCond);
 	free(r);
 }
 

@@ -7,6 +7,16 @@
 #include <zlib.h>
 
 static uint32_t be32(const unsigned char *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+/* the legal (colour type, bit depth) pairs of PNG (spec 11.2.2): gray 1/2/4/8/16, RGB 8/16, palette 1/2/4/8, gray+alpha 8/16, RGBA 8/16 */
+static int png_depth_ok(int ctype, int depth) {
+	switch (ctype) {
+	case 0: return depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16;
+	case 3: return depth == 1 || depth == 2 || depth == 4 || depth == 8;
+	case 2: case 4: case 6: return depth == 8 || depth == 16;
+	default: return 0;
+	}
+}
+
 
 static int paeth(int a, int b, int c) {
 	int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
@@ -44,7 +54,7 @@ int cr_image_decode_png(const unsigned char *buf, size_t len, struct cr_image *o
 	}
 	if (!W || !H || !z || interlace) { free(z); return -3; }             /* Adam7 is not supported */
 	const int src_n = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-	if (!src_n || (depth != 8 && depth != 16 && !(depth < 8 && (ctype == 0 || ctype == 3)))) { free(z); return -4; }
+	if (!src_n || !png_depth_ok(ctype, depth)) { free(z); return -4; }
 	const size_t bpp_bits = (size_t)src_n * (size_t)depth;
 	const size_t stride = (W * bpp_bits + 7) / 8, fbpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;
 	uLongf rawlen = (uLongf)((stride + 1) * H);
@@ -199,7 +209,7 @@ int cr_image_probe(const unsigned char *buf, size_t len) {
 	const int depth = d[8], ctype = d[9], interlace = d[12];
 	const int src_n = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
 	if (!be32(d) || !be32(d + 4) || interlace || !src_n) return 0;
-	return depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3));
+	return png_depth_ok(ctype, depth);
 }
 
 int cr_image_decode(const unsigned char *buf, size_t len, struct cr_image *out) {

@@ -112,7 +112,7 @@ def tri_rounds(meter, tris, cooperative=False):
         meter.add(W_TRI, sum(1 for t in tris if t > k))
 
 
-def simulate(rays, policy="phase", burst=3, refill=16, persistent=True, cooperative=False):
+def simulate(rays, policy="phase", burst=3, refill=16, persistent=True, cooperative=False, tburst=2):
     """Replay one K2 launch over `rays` (list of event arrays in dispatch order).  Returns (active lanes per instruction,
     instructions per ray)."""
     m = Meter()
@@ -122,6 +122,7 @@ def simulate(rays, policy="phase", burst=3, refill=16, persistent=True, cooperat
     # one persistent warp stands for all of them: the kernel's warps pull from ONE global counter in arrival order, and the
     # figure of merit is a ratio, so the interleaving of warps does not matter to first order.  (Non-persistent: a warp takes
     # 32 consecutive rays and retires when all are done.)
+    pending = {}
     while qpos < nrays:
         lanes = [None] * 32
         while True:
@@ -146,6 +147,31 @@ def simulate(rays, policy="phase", burst=3, refill=16, persistent=True, cooperat
                     codes = [r.take() for r in nodes]
                     m.add(W_NODE, len(nodes))
                     tri_rounds(m, [c - 64 for c in codes if c >= 64 and c > 64], cooperative)
+                if insts:
+                    for r in insts:
+                        r.take()
+                    m.add(W_INST, len(insts))
+            elif policy == "trimode":
+                # decoupled state machine: a lane that reaches a leaf switches to TRIANGLE mode and tests at most `tburst`
+                # triangles per outer iteration (phase T, all triangle-mode lanes together) while the other lanes keep taking
+                # node steps in phase N; it resumes traversal only when its leaf is finished (order and culling unchanged)
+                for _ in range(burst):
+                    nodes = [r for r in live if pending.get(id(r), 0) == 0 and r.wants_node()]
+                    if not nodes:
+                        break
+                    m.add(W_NODE, len(nodes))
+                    for r in nodes:
+                        c = r.take()
+                        if c > 64:
+                            pending[id(r)] = c - 64
+                for _ in range(tburst):
+                    act = [k for k, v in pending.items() if v > 0]
+                    if not act:
+                        break
+                    m.add(W_TRI + 6, len(act))
+                    for k in act:
+                        pending[k] -= 1
+                insts = [r for r in live if pending.get(id(r), 0) == 0 and r.wants_inst()]
                 if insts:
                     for r in insts:
                         r.take()
@@ -184,7 +210,7 @@ def simulate(rays, policy="phase", burst=3, refill=16, persistent=True, cooperat
                     for r in insts:
                         r.take()
                     m.add(W_INST, len(insts))
-            fin = [i for i, r in enumerate(lanes) if r is not None and r.done()]
+            fin = [i for i, r in enumerate(lanes) if r is not None and r.done() and pending.get(id(r), 0) == 0]
             if fin:
                 m.add(W_WRITEBACK, len(fin))
                 for i in fin:
@@ -230,6 +256,10 @@ def main():
             ("leaves wait, burst 8, refill<24", dict(policy="leafwait", burst=8, refill=24)),
             ("leaves wait, burst 8 + cooperative triangles", dict(policy="leafwait", burst=8, refill=16, cooperative=True)),
             ("  refill<31 + cooperative triangles", dict(policy="phase", burst=3, refill=31, cooperative=True)),
+            ("triangle MODE (decoupled), burst 3, 1 tri per iteration", dict(policy="trimode", burst=3, refill=16, tburst=1)),
+            ("triangle MODE, burst 3, 2 tris per iteration", dict(policy="trimode", burst=3, refill=16, tburst=2)),
+            ("triangle MODE, burst 3, 4 tris per iteration", dict(policy="trimode", burst=3, refill=16, tburst=4)),
+            ("triangle MODE, burst 2, 2 tris, refill<24", dict(policy="trimode", burst=2, refill=24, tburst=2)),
         ]
         for name, kw in rows:
             act, ipr = simulate(rays, **kw)
