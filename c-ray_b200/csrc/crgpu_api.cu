@@ -139,6 +139,7 @@ struct crgpu_prepared {
 	int32_t background;
 	uint32_t instance_count;
 	DevBvh top;
+	float world_lo[3], world_inv[3];
 	uint32_t stage_pairs;
 	uint32_t texture_count;
 	uint8_t *slab;
@@ -165,8 +166,12 @@ struct crgpu_scene {
 	uint64_t max_paths;
 	uint64_t cap_paths;        /* capacity of the wavefront buffers */
 	void *wave; size_t wave_bytes;
-	WaveBuffers wb;
+	int wave_sets;             /* 1, or 2 when batches are overlapped on two streams (each set holds cap_paths paths) */
+	WaveBuffers wb;            /* set 0 */
+	WaveBuffers wb2;           /* set 1: own ray / hit / radiance buffers and own hist + counts; stats shared */
+	cudaStream_t stream2;      /* the second stream of overlapped batches */
 	cudaEvent_t ev[4];
+	cudaEvent_t evAcc[2], evFork;   /* accumulate-order chain between the two streams */
 	uint32_t *pixels;          /* device pixel list of the last crgpu_render_tiles tile set */
 	size_t pixel_cap;
 	std::vector<int> pixel_key;
@@ -342,28 +347,35 @@ static int build_pairs(const crs_scene *f, const crs_bvh &b, std::vector<PairNod
 static inline void f3(float *dst, const float *src, size_t idx) { dst[0] = src[3 * idx]; dst[1] = src[3 * idx + 1]; dst[2] = src[3 * idx + 2]; }
 
 /* all wavefront buffers of a scene are carved from ONE device block (one cudaMalloc / one cache hit per frame) */
-static int alloc_wave(crgpu_scene *s, uint64_t paths) {
-	if (paths <= s->cap_paths) return CRGPU_OK;
-	WaveBuffers &w = s->wb;
-	if (s->wave) ctx_free(s->device, s->wave, s->wave_bytes);
-	s->wave = nullptr; s->wave_bytes = 0; s->cap_paths = 0;
+static int alloc_wave(crgpu_scene *s, uint64_t paths, int sets) {
+	if (paths <= s->cap_paths && sets <= s->wave_sets) return CRGPU_OK;
+	if (s->wave) {
+		cudaStreamSynchronize(s->stream);                           /* queued kernels may still use the old block */
+		if (s->stream2) cudaStreamSynchronize(s->stream2);
+		ctx_free(s->device, s->wave, s->wave_bytes);
+	}
+	s->wave = nullptr; s->wave_bytes = 0; s->cap_paths = 0; s->wave_sets = 0;
 	const size_t n = ((size_t)paths + 255u) & ~(size_t)255u;      /* every sub-array stays 256-byte aligned */
-	const size_t bytes = n * (9u * 16u + 2u * 4u + 1u);
+	const size_t per_set = n * (9u * 16u + 2u * 4u + 1u);         /* 153 B per path */
+	const size_t bytes = per_set * (size_t)sets;
 	void *base = nullptr;
 	int rc = ctx_alloc(s->device, bytes, &base);
 	if (rc) return rc;
 	s->wave = base; s->wave_bytes = bytes;
-	uint8_t *q = static_cast<uint8_t *>(base);
-	auto take = [&](size_t b) { uint8_t *r = q; q += b; return r; };
-	w.stA[0] = (float4 *)take(n * 16); w.stA[1] = (float4 *)take(n * 16);
-	w.stB[0] = (float4 *)take(n * 16); w.stB[1] = (float4 *)take(n * 16);
-	w.stC[0] = (uint4 *)take(n * 16); w.stC[1] = (uint4 *)take(n * 16);
-	w.hit = (float4 *)take(n * 16); w.L = (float4 *)take(n * 16);
-	w.hitInst = (int *)take(n * 4); w.perm = (unsigned *)take(n * 4);
-	w.hitKey = (unsigned char *)take(n);
-	w.perm2 = (unsigned *)take(n * 4); w.dirKey = (unsigned char *)take(n);
-	take(n * 11);                                                  /* spare 16-B lane (keeps the block size a round 137 -> 153 B/path) */
+	for (int k = 0; k < sets; ++k) {
+		WaveBuffers &w = k ? s->wb2 : s->wb;
+		uint8_t *q = static_cast<uint8_t *>(base) + per_set * (size_t)k;
+		auto take = [&](size_t b) { uint8_t *r = q; q += b; return r; };
+		w.stA[0] = (float4 *)take(n * 16); w.stA[1] = (float4 *)take(n * 16);
+		w.stB[0] = (float4 *)take(n * 16); w.stB[1] = (float4 *)take(n * 16);
+		w.stC[0] = (uint4 *)take(n * 16); w.stC[1] = (uint4 *)take(n * 16);
+		w.hit = (float4 *)take(n * 16); w.L = (float4 *)take(n * 16);
+		w.hitInst = (int *)take(n * 4); w.perm = (unsigned *)take(n * 4);
+		w.hitKey = (unsigned char *)take(n);
+		w.perm2 = (unsigned *)take(n * 4); w.dirKey = (unsigned char *)take(n);
+	}
 	s->cap_paths = paths;
+	s->wave_sets = sets;
 	return CRGPU_OK;
 }
 
@@ -372,6 +384,7 @@ extern "C" int crgpu_scene_destroy(crgpu_scene *s) {
 	cudaSetDevice(s->device);
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	if (s->own_stream && s->own_stream != s->stream) cudaStreamSynchronize(s->own_stream);
+	if (s->stream2) cudaStreamSynchronize(s->stream2);
 	ctx_free(s->device, s->slab, s->slab_bytes);
 	ctx_free(s->device, s->wave, s->wave_bytes);
 	ctx_free(s->device, s->small, s->small_bytes);
@@ -379,6 +392,9 @@ extern "C" int crgpu_scene_destroy(crgpu_scene *s) {
 	ctx_free(s->device, s->fb8, s->fb_floats);
 	ctx_free(s->device, s->pixels, s->pixel_cap * sizeof(uint32_t));
 	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : s->evAcc) if (e) cudaEventDestroy(e);
+	if (s->evFork) cudaEventDestroy(s->evFork);
+	if (s->stream2) cudaStreamDestroy(s->stream2);
 	if (s->own_stream) cudaStreamDestroy(s->own_stream);
 	delete s;
 	return CRGPU_OK;
@@ -621,7 +637,7 @@ extern "C" int crgpu_prepare(const struct crs_scene *f, crgpu_prepared **out) {
 		/* shared memory and L1 share 228 KB per SM: every staged KB is a KB of L1 the traversal loses, so the default
 		 * stages only the very top (128 nodes = 8 KB); CRGPU_TRACE_STAGE=<pairs> (0..1024) overrides */
 		const char *env = getenv("CRGPU_TRACE_STAGE");
-		uint32_t total_budget = env ? (uint32_t)atoi(env) : 128u;
+		uint32_t total_budget = env ? (uint32_t)atoi(env) : 0u;
 		if (total_budget > CRG_STAGE_PAIRS) total_budget = CRG_STAGE_PAIRS;
 		take(bvhs[f->top_bvh], total_budget / 4);
 		uint64_t total_internal = 0;
@@ -635,6 +651,19 @@ extern "C" int crgpu_prepare(const struct crs_scene *f, crgpu_prepared **out) {
 	}
 	p->top = bvhs[f->top_bvh];
 	p->stage_pairs = (uint32_t)stage.size();
+	{	/* world bounds = bounds of the top-level BVH root (both children of pair 0, or the single leaf's box) */
+		float lo[3] = { 0.f, 0.f, 0.f }, hi[3] = { 1.f, 1.f, 1.f };
+		const crs_bvh &tb = f->bvhs[f->top_bvh];
+		if (tb.node_count >= 1) {
+			const float *b = f->bvh_nodes[tb.node_offset].bounds;          /* minx,maxx,miny,maxy,minz,maxz */
+			for (int k = 0; k < 3; ++k) { lo[k] = b[2 * k]; hi[k] = b[2 * k + 1]; }
+		}
+		for (int k = 0; k < 3; ++k) {
+			const float e = hi[k] - lo[k];
+			p->world_lo[k] = lo[k];
+			p->world_inv[k] = (e > 0.f && e < 3.0e38f) ? 1.0f / e : 0.f;
+		}
+	}
 	std::vector<float> lut(256);
 	for (int i = 0; i < 256; ++i) { volatile float num = (float)i, den = 255.0f; lut[i] = num / den; }   /* IEEE divss == __fdiv_rn */
 
@@ -682,6 +711,8 @@ extern "C" int crgpu_scene_create_prepared(const crgpu_prepared *p, int device, 
 	crgpu_scene *s = new crgpu_scene();
 	memset(&s->dev, 0, sizeof s->dev);
 	memset(&s->wb, 0, sizeof s->wb);
+	memset(&s->wb2, 0, sizeof s->wb2);
+	s->wave_sets = 0; s->stream2 = nullptr; s->evAcc[0] = s->evAcc[1] = nullptr; s->evFork = nullptr;
 	s->pixels = nullptr; s->pixel_cap = 0;
 	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->own_stream = nullptr; s->cap_paths = 0;
 	s->slab = nullptr; s->slab_bytes = 0; s->small = nullptr; s->small_bytes = 0; s->wave = nullptr; s->wave_bytes = 0; s->fb_floats = 0;
@@ -695,6 +726,9 @@ extern "C" int crgpu_scene_create_prepared(const crgpu_prepared *p, int device, 
 	CUS(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
 	s->stream = s->own_stream;
 	for (auto &e : s->ev) CUS(cudaEventCreate(&e));
+	CUS(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+	for (auto &e : s->evAcc) CUS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	CUS(cudaEventCreateWithFlags(&s->evFork, cudaEventDisableTiming));
 
 	/* the scene: one block, one copy */
 	FAIL_IF(ctx_alloc(device, p->slab_bytes, &s->slab));
@@ -720,6 +754,7 @@ extern "C" int crgpu_scene_create_prepared(const crgpu_prepared *p, int device, 
 	d.instance_count = p->instance_count;
 	d.top = p->top;
 	d.stage_pairs = p->stage_pairs;
+	memcpy(d.world_lo, p->world_lo, sizeof d.world_lo); memcpy(d.world_inv, p->world_inv, sizeof d.world_inv);
 	d.stage_img = reinterpret_cast<const PairNode *>(base + p->off[SEC_STAGE]);
 	d.pairs = reinterpret_cast<const PairNode *>(base + p->off[SEC_PAIRS]);
 	d.tris = reinterpret_cast<const PackedTri *>(base + p->off[SEC_TRIS]);
@@ -739,12 +774,18 @@ extern "C" int crgpu_scene_create_prepared(const crgpu_prepared *p, int device, 
 	s->fb_floats = (size_t)d.image_width * d.image_height * 3u;
 	{ void *q = nullptr; FAIL_IF(ctx_alloc(device, s->fb_floats * sizeof(float), &q)); s->fb = static_cast<float *>(q); }
 	CUS(cudaMemsetAsync(s->fb, 0, s->fb_floats * sizeof(float), s->stream));
-	s->small_bytes = 1024 * sizeof(unsigned) + 256 + 80 * sizeof(unsigned long long);
-	FAIL_IF(ctx_alloc(device, s->small_bytes, &s->small));
-	CUS(cudaMemsetAsync(s->small, 0, s->small_bytes, s->stream));
-	s->wb.hist = static_cast<unsigned *>(s->small);
-	s->wb.counts = s->wb.hist + 1024;
-	s->wb.stats = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(s->small) + 1024 * sizeof(unsigned) + 256);
+	{	/* per wave set: hist[1024] + counts[64]; then the shared stats[80] */
+		const size_t set_bytes = 1024 * sizeof(unsigned) + 256;
+		s->small_bytes = 2 * set_bytes + 80 * sizeof(unsigned long long);
+		FAIL_IF(ctx_alloc(device, s->small_bytes, &s->small));
+		CUS(cudaMemsetAsync(s->small, 0, s->small_bytes, s->stream));
+		uint8_t *sm = static_cast<uint8_t *>(s->small);
+		s->wb.hist = reinterpret_cast<unsigned *>(sm);
+		s->wb.counts = s->wb.hist + 1024;
+		s->wb2.hist = reinterpret_cast<unsigned *>(sm + set_bytes);
+		s->wb2.counts = s->wb2.hist + 1024;
+		s->wb.stats = s->wb2.stats = reinterpret_cast<unsigned long long *>(sm + 2 * set_bytes);
+	}
 	{
 		/* Paths in flight per wavefront batch.  Every batch pays a fixed ~7 ms (the serial chain of its bounces: each
 		 * late bounce lasts as long as its slowest ray), so batches should be as large as memory allows:
@@ -823,47 +864,74 @@ static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, in
 		if (flags & CRGPU_FLAG_ASYNC) return CRGPU_OK;
 		return crgpu_get_stats(s, stats);
 	}
-	uint64_t batch = s->max_paths / tile_pixels;
-	if (batch > (uint64_t)pass_count) batch = (uint64_t)pass_count;
-	if (batch < 1) batch = 1;
-	int rc = alloc_wave(s, tile_pixels * batch);
-	if (rc) return rc;
-
-	cudaStream_t st = s->stream;
 	const bool count = (flags & CRGPU_FLAG_COUNT) != 0;
 	const bool timing = (flags & CRGPU_FLAG_TIME_KERNELS) != 0;
+	/* Batches.  A batch pays a fixed cost of several ms: its bounces 5..12 hold too few rays to fill 148 SMs, and every bounce lasts
+	 * as long as its slowest ray.  So (1) batches are as large as the path budget allows and of EQUAL size (a 987 + 13 split wastes
+	 * a whole tail on 13 passes), and (2) with two or more batches the budget is split into two wave sets that run on two streams:
+	 * the thin tail of one batch overlaps the fat first bounces of the next.  Only the accumulate step is ordered (the running
+	 * average is taken in pass order, renderer.c:288-291): batch b's k_accumulate waits for batch b-1's.  CRGPU_OVERLAP=0 disables. */
+	static const int overlap_on = [] { const char *e = getenv("CRGPU_OVERLAP"); return e ? atoi(e) : 1; }();
+	uint64_t batch = s->max_paths / tile_pixels;
+	if (batch < 1) batch = 1;
+	int sets = 1;
+	if (overlap_on && !timing && !count && batch < (uint64_t)pass_count && batch >= 2) { sets = 2; batch /= 2; }
+	if (batch > (uint64_t)pass_count) batch = (uint64_t)pass_count;
+	{
+		const uint64_t nb = ((uint64_t)pass_count + batch - 1) / batch;
+		if (nb > 0) batch = ((uint64_t)pass_count + nb - 1) / nb;   /* equal shares */
+		if (batch < 1) batch = 1;
+	}
+	int rc = alloc_wave(s, tile_pixels * batch, sets);
+	if (rc) return rc;
+
 	const int maxDepth = (int)s->dev.bounces;
 	const int grid = s->sm_count * 8;
 	const int dirmode = crg_dir_mode();
 	uint64_t launches = 0;
 	float trace_ms = 0.f, shade_ms = 0.f;
-	if (timing) CU(cudaEventRecord(s->ev[0], st));
+	if (timing) CU(cudaEventRecord(s->ev[0], s->stream));
 	std::vector<cudaEvent_t> tev;   /* per-kernel events when timing */
-	for (int pb = pass_begin; pb < pass_begin + pass_count; pb += (int)batch) {
+	if (sets == 2) {                /* fork: the second stream starts behind whatever is queued on the first */
+		CU(cudaEventRecord(s->evFork, s->stream));
+		CU(cudaStreamWaitEvent(s->stream2, s->evFork, 0));
+	}
+	int bi = 0;
+	for (int pb = pass_begin; pb < pass_begin + pass_count; pb += (int)batch, ++bi) {
+		const int set = sets == 2 ? (bi & 1) : 0;
+		cudaStream_t st = set ? s->stream2 : s->stream;
+		const WaveBuffers &wb = set ? s->wb2 : s->wb;
 		TileDesc td = base;
 		td.npix = (unsigned)tile_pixels;
 		td.pass_begin = pb;
 		td.pass_count = (pass_begin + pass_count - pb) < (int)batch ? (pass_begin + pass_count - pb) : (int)batch;
-		crg_launch_generate(s->dev, s->wb, td, grid, st); ++launches;
+		crg_launch_generate(s->dev, wb, td, grid, st); ++launches;
 		/* bounces == 0: pathTrace's loop never runs and every sample is black (pathtrace.c:34-36,59).  L is write-once by
 		 * design (cr_add_radiance / cr_finish_path), so with no bounce nothing would write it: clear it here instead */
-		if (maxDepth == 0) CU(cudaMemsetAsync(s->wb.L, 0, (size_t)tile_pixels * (size_t)td.pass_count * sizeof(float4), st));
+		if (maxDepth == 0) CU(cudaMemsetAsync(wb.L, 0, (size_t)tile_pixels * (size_t)td.pass_count * sizeof(float4), st));
 		int cur = 0;
 		for (int depth = 0; depth < maxDepth; ++depth) {
-			if (depth >= CRG_TAIL_FROM && !count) { crg_launch_tail(s->dev_copy, s->wb, cur, depth, maxDepth, st); ++launches; }
+			if (depth >= CRG_TAIL_FROM && !count) { crg_launch_tail(s->dev_copy, wb, cur, depth, maxDepth, st); ++launches; }
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
-			crg_launch_trace(s->dev, s->wb, cur, count, dirmode != 0 && depth > 0, grid, st);
+			crg_launch_trace(s->dev, wb, cur, count, dirmode != 0 && depth > 0, grid, st);
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
-			crg_launch_bucket(s->wb, cur, grid, st);
+			crg_launch_bucket(wb, cur, grid, st);
 			const bool sort_next = dirmode != 0 && depth + 1 < maxDepth;
-			crg_launch_shade(s->dev_copy, s->wb, cur, depth, maxDepth, sort_next ? dirmode : 0, grid, st);
-			if (sort_next) { crg_launch_dirsort(s->wb, cur ^ 1, grid, st); ++launches; }    /* K4b: the next bounce's rays by direction bin */
+			crg_launch_shade(s->dev_copy, wb, cur, depth, maxDepth, sort_next ? dirmode : 0, grid, st);
+			if (sort_next) { crg_launch_dirsort(wb, cur ^ 1, grid, st); ++launches; }    /* K4b: the next bounce's rays by direction bin */
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
 			launches += 2 + (uint64_t)crg_shade_launches_per_bounce();
 			cur ^= 1;
 		}
-		crg_launch_accumulate(s->fb, s->wb.L, td, (int)s->dev.image_width, (int)s->dev.image_height, grid, st); ++launches;
+		if (sets == 2 && bi > 0) CU(cudaStreamWaitEvent(st, s->evAcc[set ^ 1], 0));      /* pass order of the running average */
+		crg_launch_accumulate(s->fb, wb.L, td, (int)s->dev.image_width, (int)s->dev.image_height, grid, st); ++launches;
+		if (sets == 2) CU(cudaEventRecord(s->evAcc[set], st));
 	}
+	if (sets == 2 && bi > 0) {      /* join: everything queued later on the scene's stream comes after both */
+		CU(cudaStreamWaitEvent(s->stream, s->evAcc[(bi - 1) & 1], 0));
+		if (bi > 1) CU(cudaStreamWaitEvent(s->stream, s->evAcc[bi & 1], 0));
+	}
+	cudaStream_t st = s->stream;
 	if (timing) CU(cudaEventRecord(s->ev[1], st));
 	CU(cudaGetLastError());
 	s->pend_paths += tile_pixels * (uint64_t)pass_count;

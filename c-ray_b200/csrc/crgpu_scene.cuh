@@ -109,4 +109,5 @@ struct DevScene {
 	                                   TMA bulk copy (cp.async.bulk) per block; stage_pairs = number of nodes in it */
 	uint32_t          stage_pairs;
 	const float      *u8_to_unit;   /* [256]: (float)i / 255.0f, the byte→float division of texture.c:48-60 done once */
+	float             world_lo[3], world_inv[3];   /* top-level BVH bounds: lower corner and 1/extent (only used to BIN rays by origin cell, K4b) */
 };

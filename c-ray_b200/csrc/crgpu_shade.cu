@@ -107,12 +107,16 @@ CRD bool cr_shade_one(const DevScene &sc, float4 *__restrict__ Lbuf, v3 o, v3 d,
 
 /* direction bin of a ray for K4b: sign octant (bvh.c:370-372 picks the near/far planes from exactly these bits), optionally
  * times the major axis.  Any binning is legal: the order rays are traced in never changes a result. */
-CRD unsigned cr_dir_bin(v3 d, int mode) {
+CRD unsigned cr_dir_bin(const DevScene &sc, v3 o, v3 d, int mode) {
 	unsigned key = (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
-	if (mode >= 2) {
+	if (mode == 2) {
 		const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
 		const unsigned major = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
 		key |= major << 3;                       /* 0..23 */
+	} else if (mode == 3) {                      /* + origin cell in the world box: 4 x 2 x 4 cells -> 256 bins */
+		const float fx = (o.x - sc.world_lo[0]) * sc.world_inv[0], fy = (o.y - sc.world_lo[1]) * sc.world_inv[1], fz = (o.z - sc.world_lo[2]) * sc.world_inv[2];
+		const unsigned cx = (unsigned)fminf(fmaxf(fx * 4.0f, 0.0f), 3.0f), cy = (unsigned)fminf(fmaxf(fy * 2.0f, 0.0f), 1.0f), cz = (unsigned)fminf(fmaxf(fz * 4.0f, 0.0f), 3.0f);
+		key |= (cx << 3) | (cz << 5) | (cy << 7);
 	}
 	return key;
 }
@@ -140,8 +144,8 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 		}
 		return;
 	}
-	__shared__ unsigned s_dir[32];                                /* direction-bin sizes of the rays this block writes */
-	if (threadIdx.x < 32) s_dir[threadIdx.x] = 0u;
+	__shared__ unsigned s_dir[256];                               /* direction-bin sizes of the rays this block writes (blockDim.x == 256) */
+	s_dir[threadIdx.x] = 0u;
 	__syncthreads();
 	if (blockIdx.x == 0 && threadIdx.x == 0) wb.counts[2] = 0u;   /* K2's work counter, for the next bounce */
 	if (blockIdx.x == 0) { wb.hist[threadIdx.x] = 0u; wb.hist[256 + threadIdx.x] = 0u; }   /* K2/K4 histogram + cursors (blockDim.x == 256) */
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 				wb.stB[nxt][k] = make_float4(d_next.y, d_next.z, wr, wg);
 				wb.stC[nxt][k] = make_uint4(__float_as_uint(wbl), id, (unsigned)(rng & 0xffffffffull), (unsigned)(rng >> 32));
 				if (dirmode) {
-					const unsigned key = cr_dir_bin(d_next, dirmode);
+					const unsigned key = cr_dir_bin(sc, p_next, d_next, dirmode);
 					wb.dirKey[k] = (unsigned char)key;
 					atomicAdd(&s_dir[key], 1u);
 				}
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 	}
 	if (dirmode) {
 		__syncthreads();
-		if (threadIdx.x < 32 && s_dir[threadIdx.x]) atomicAdd(&wb.hist[512 + threadIdx.x], s_dir[threadIdx.x]);
+		if (s_dir[threadIdx.x]) atomicAdd(&wb.hist[512 + threadIdx.x], s_dir[threadIdx.x]);
 	}
 }
 
@@ -320,7 +324,7 @@ void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int de
 /* CRGPU_SHADE_MINB = 2|3|4 (blocks per SM of the hit/all kernel: 128 / 80 / 64 registers), CRGPU_SHADE_SPLIT = 0|1 (separate
  * miss kernel at 4 blocks per SM) — read once; the defaults are what measured best on hdr.json / venus.json (profiles/) */
 void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int dirmode, int grid, cudaStream_t st) {
-	static const int minb = [] { const char *e = getenv("CRGPU_SHADE_MINB"); const int v = e ? atoi(e) : 2; return v >= 2 && v <= 4 ? v : 2; }();
+	static const int minb = [] { const char *e = getenv("CRGPU_SHADE_MINB"); const int v = e ? atoi(e) : 3; return v >= 2 && v <= 4 ? v : 3; }();
 	static const int split = [] { const char *e = getenv("CRGPU_SHADE_SPLIT"); return e ? atoi(e) : 1; }();
 	if (split) {
 		k_shade<4, 1><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
@@ -337,7 +341,7 @@ void crg_launch_dirsort(const WaveBuffers &wb, int nxt, int grid, cudaStream_t s
 	k_bucket<true><<<grid, 256, 0, st>>>(wb, nxt);
 }
 int crg_dir_mode(void) {
-	static const int mode = [] { const char *e = getenv("CRGPU_TRACE_SORT"); const int v = e ? atoi(e) : 1; return v >= 0 && v <= 2 ? v : 1; }();
+	static const int mode = [] { const char *e = getenv("CRGPU_TRACE_SORT"); const int v = e ? atoi(e) : 0; return v >= 0 && v <= 3 ? v : 0; }();
 	return mode;
 }
 int crg_shade_launches_per_bounce(void) { const char *e = getenv("CRGPU_SHADE_SPLIT"); return (e ? atoi(e) : 1) ? 2 : 1; }

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
 #define CRG_MAX_STEPS 8000000u   /* > 30x the node count of any scene that fits the 2^23-node address space we support */
 
 template <bool COUNT, int MINB, bool DEFER>
-__global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb, int cur, int refill, int burst, int sorted) {
+__global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb, int cur, int refill, int burst, int sorted, int inst_min) {
 	const unsigned n = wb.counts[cur];
 	const unsigned lane = threadIdx.x & 31u;
 	const float4 *__restrict__ stA = wb.stA[cur];
@@ -137,8 +137,19 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 		}
 		/* Phase T (DEFER): the triangles of every lane that reached a leaf during the burst, together */
 		if (DEFER && busy && tr.wants_leaf()) tr.leaf_step(sc, &tc);
-		/* Phase I: one pending instance (ray transform + sphere test, or entry into a mesh BVH) */
-		if (busy && tr.wants_instance()) { tr.instance_step(sc, &tc); ++steps; }
+		/* Phase I: one pending instance (ray transform + sphere test, or entry into a mesh BVH).  ncu (profiles/r01: 19.8% of K2's
+		 * warp instructions ran with fewer than 2 active lanes, almost all of them here): lanes reach a top-level leaf at different
+		 * iterations, so running this ~100-instruction block whenever ANY lane wants it means running it for one lane.  Lanes
+		 * therefore WAIT here until at least `inst_min` of them want an instance step, or no lane of the warp can take a node step. */
+		{
+			const bool wi = busy && tr.wants_instance();
+			const unsigned mi = __ballot_sync(0xffffffffu, wi);
+			if (mi) {
+				bool go = (int)__popc(mi) >= inst_min;
+				if (!go) go = !__any_sync(0xffffffffu, busy && tr.wants_node());
+				if (go && wi) { tr.instance_step(sc, &tc); ++steps; }
+			}
+		}
 		/* Phase W: write back finished rays */
 		if (busy && tr.done()) {
 			wb.hit[ray] = make_float4(tr.best.t, tr.best.u, tr.best.v, __uint_as_float(tr.best.prim));
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 		atomicAdd(&wb.stats[4], (unsigned long long)tc.insts);
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		wb.stats[0] += n;          /* one ray per getClosestIsect */
+		atomicAdd(&wb.stats[0], (unsigned long long)n);          /* one ray per getClosestIsect (two streams may run two K2s) */
 		wb.counts[cur ^ 1] = 0u;   /* K3 of this bounce appends survivors there */
 	}
 }
@@ -212,13 +223,14 @@ static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int 
 	}
 	static const int refill = [] { const char *e = getenv("CRGPU_TRACE_REFILL"); const int v = e ? atoi(e) : CRG_REFILL; return v >= 1 && v <= 32 ? v : CRG_REFILL; }();
 	static const int burst = [] { const char *e = getenv("CRGPU_TRACE_BURST"); const int v = e ? atoi(e) : (DEFER ? 4 : CRG_NODE_BURST); return v >= 1 ? v : CRG_NODE_BURST; }();
-	k_trace<COUNT, MINB, DEFER><<<grid, 256, smem, st>>>(sc, wb, cur, refill, burst, sorted ? 1 : 0);
+	static const int inst_min = [] { const char *e = getenv("CRGPU_TRACE_INSTMIN"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 32 ? v : 8; }();
+	k_trace<COUNT, MINB, DEFER><<<grid, 256, smem, st>>>(sc, wb, cur, refill, burst, sorted ? 1 : 0, inst_min);
 }
 
 void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, bool sorted, int grid, cudaStream_t st) {
 	(void)grid;
 	static const int minb = [] { const char *e = getenv("CRGPU_TRACE_MINB"); const int v = e ? atoi(e) : 3; return v >= 2 && v <= 4 ? v : 3; }();
-	static const int defer = [] { const char *e = getenv("CRGPU_TRACE_DEFER"); return e ? atoi(e) : 1; }();
+	static const int defer = [] { const char *e = getenv("CRGPU_TRACE_DEFER"); return e ? atoi(e) : 0; }();
 	if (count) { if (defer) launch_trace_variant<true, 3, true>(sc, wb, cur, sorted, st); else launch_trace_variant<true, 3, false>(sc, wb, cur, sorted, st); return; }
 	if (defer) {
 		if (minb == 4) launch_trace_variant<false, 4, true>(sc, wb, cur, sorted, st);

@@ -60,7 +60,7 @@ void crg_launch_pixel_list(uint32_t *pixels, const int4 *rects, const unsigned *
 void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDesc &td, int grid, cudaStream_t st);
 void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, bool sorted, int grid, cudaStream_t st);
 void crg_launch_dirsort(const WaveBuffers &wb, int nxt, int grid, cudaStream_t st);
-int crg_dir_mode(void);   /* 0 = off, 1 = octant (8 bins), 2 = octant x major axis (24 bins) */
+int crg_dir_mode(void);   /* 0 = off, 1 = octant (8 bins), 2 = octant x major axis (24 bins), 3 = octant x origin cell (256 bins) */
 void crg_launch_bucket(const WaveBuffers &wb, int cur, int grid, cudaStream_t st);
 void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, cudaStream_t st);
 void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int dirmode, int grid, cudaStream_t st);
