@@ -35,6 +35,8 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned f) { (void)f; *s
 cudaError_t cudaStreamDestroy(cudaStream_t s) { (void)s; return 0; }
 cudaError_t cudaStreamSynchronize(cudaStream_t s) { (void)s; return 0; }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (void *)1; return 0; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned f) { (void)f; *e = (void *)1; return 0; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned f) { (void)s; (void)e; (void)f; return 0; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { (void)e; return 0; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { (void)e; (void)s; return 0; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { (void)a; (void)b; *ms = 0; return 0; }
