@@ -19,7 +19,8 @@ import pytest
 import conftest
 from conftest import BUILT, ROOT
 
-FULL = [("hdr", 1920, 1080, 1000, 32), ("refraction", 1920, 1080, 2500, 512), ("venus", 2560, 1600, 1000, 25)]
+FULL = [("hdr", 1920, 1080, 1000, 32), ("refraction", 1920, 1080, 64, 512), ("venus", 2560, 1600, 32, 25),
+        ("refraction", 1920, 1080, 2500, 512), ("venus", 2560, 1600, 1000, 25)]
 
 
 def compare_frames(gpu, ref):
