@@ -864,6 +864,10 @@ static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, in
 		if (flags & CRGPU_FLAG_ASYNC) return CRGPU_OK;
 		return crgpu_get_stats(s, stats);
 	}
+	if (pass_count == 0 || tile_pixels == 0) {          /* an empty pass range is a no-op (and must not reach the batch arithmetic below) */
+		if (flags & CRGPU_FLAG_ASYNC) return CRGPU_OK;
+		return crgpu_get_stats(s, stats);
+	}
 	const bool count = (flags & CRGPU_FLAG_COUNT) != 0;
 	const bool timing = (flags & CRGPU_FLAG_TIME_KERNELS) != 0;
 	/* Batches.  A batch pays a fixed cost of several ms: its bounces 5..12 hold too few rays to fill 148 SMs, and every bounce lasts
