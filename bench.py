@@ -355,7 +355,11 @@ def main():
     clocks = sampler.summary()
     value_crc = zlib.crc32(g.read().tobytes()) if rank == 0 else 0
     tms = torch.tensor([ms, float(stats["rays"]), float(stats["paths"]), float(stats["kernel_launches"])], device=dev, dtype=torch.float64)
+    rank_ms = [float(tms[0])]
     if dist:
+        allms = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allms, tms[:1].clone())
+        rank_ms = [round(float(x[0]) / args.steps, 3) for x in allms]     # per-rank device time per step: tile imbalance shows here
         mx = tms.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tms.clone()
@@ -459,7 +463,7 @@ def main():
                 "config": {"workload": f"input/{w['scene']}.json {W}x{H} {spp} spp {bounces} bounces", "name": args.workload, "tile": tile,
                            "parallelism": f"tile-sharded x{world} (queue position % world), one NCCL gather per frame" if world > 1 else "1 GPU",
                            "l2": "wavefront state (GBs per step) streams through the 126 MB L2: inputs larger than L2, no explicit flush"},
-                "msample_per_s": round(msample, 2), "rays_per_sample": round(rays / paths, 4),
+                "msample_per_s": round(msample, 2), "rays_per_sample": round(rays / paths, 4), "rank_ms_per_step": rank_ms if world > 1 else None,
                 "e2e": {"value": round(e2e_value, 2), "unit": "Mray/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * W * 3 * 4 + H * W * 3,
                         "ms_per_step": round(e_ms / e_steps, 3), "steps": e_steps,
                         "what": "libcrhost.so renderFrame: prepared scene (pinned host) -> H2D -> tiles through the C dispatcher -> NCCL gather (C) -> "

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) k_bucket(WaveBuffers wb, int cur) {
  * of the carried id remembers that L holds a value; a path that ends without any contribution writes zeros.  So K1
  * never has to clear L and most paths touch their L record exactly once. */
 #define CRG_ID_HAS_L 0x80000000u
+CRD void crg_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 CRD void cr_add_radiance(float4 *__restrict__ Lbuf, unsigned &id, float r, float g, float b) {
 	const unsigned slot = id & ~CRG_ID_HAS_L;
@@ -126,7 +127,7 @@ CRD unsigned cr_dir_bin(const DevScene &sc, v3 o, v3 d, int mode) {
  * background lookup + radiance, the path always ends, nothing to compact), 2 = the hits (perm[counts[4] .. n)).  The miss half
  * needs a third of the registers of the hit half, so it runs at twice the occupancy; on hdr.json 40% of all rays are misses. */
 template <int MINB, int PART>
-__global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth, int dirmode) {
+__global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth, int dirmode, int prefetch) {
 	const DevScene &sc = *scp;
 	const unsigned n = wb.counts[cur];
 	const int nxt = cur ^ 1;
@@ -153,14 +154,23 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 	/* whole warps iterate together so the ballot below is convergent */
 	const unsigned first = PART == 2 ? wb.counts[4] : 0u;
 	const unsigned nround = first + ((n - first + 31u) & ~31u);
-	for (unsigned j = first + blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += stride) {
+	/* perm is read two iterations ahead and the records it points to one iteration ahead (crg_prefetch_l2): the five 16-B gathers
+	 * through perm are the DRAM-latency loads of this loop (the scene itself is L2-resident), so they are L2 hits when needed */
+	unsigned j0 = first + blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned i_cur = (prefetch && j0 < n) ? wb.perm[j0] : 0u, i_nxt = (prefetch && j0 + stride < n) ? wb.perm[j0 + stride] : 0u;
+	for (unsigned j = j0; j < nround; j += stride) {
+		const unsigned i_n2 = (prefetch && j + 2u * stride < n && j + 2u * stride > j) ? wb.perm[j + 2u * stride] : 0u;
 		bool alive = false;
 		v3 p_next = v3make(0, 0, 0), d_next = v3make(0, 0, 0);
 		float wr = 0.f, wg = 0.f, wbl = 0.f;
 		unsigned id = 0u;
 		uint64_t rng = 0ull;
 		if (j < n) {
-			const unsigned i = wb.perm[j];                       /* bucket order: a warp shades one material */
+			const unsigned i = prefetch ? i_cur : wb.perm[j];     /* bucket order: a warp shades one material */
+			if (prefetch && j + stride < n) {
+				crg_prefetch_l2(&wb.stA[cur][i_nxt]); crg_prefetch_l2(&wb.stB[cur][i_nxt]); crg_prefetch_l2(&wb.stC[cur][i_nxt]);
+				crg_prefetch_l2(&wb.hit[i_nxt]); crg_prefetch_l2(&wb.hitInst[i_nxt]);
+			}
 			const float4 a = wb.stA[cur][i];
 			const float4 b = wb.stB[cur][i];
 			const uint4 c = wb.stC[cur][i];
@@ -191,6 +201,7 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 				}
 			}
 		}
+		i_cur = i_nxt; i_nxt = i_n2;
 	}
 	if (dirmode) {
 		__syncthreads();
@@ -326,16 +337,17 @@ void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int de
 void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int dirmode, int grid, cudaStream_t st) {
 	static const int minb = [] { const char *e = getenv("CRGPU_SHADE_MINB"); const int v = e ? atoi(e) : 3; return v >= 2 && v <= 4 ? v : 3; }();
 	static const int split = [] { const char *e = getenv("CRGPU_SHADE_SPLIT"); return e ? atoi(e) : 1; }();
+	static const int prefetch = [] { const char *e = getenv("CRGPU_SHADE_PREFETCH"); return e ? atoi(e) : 0; }();
 	if (split) {
-		k_shade<4, 1><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
-		if (minb == 3) k_shade<3, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
-		else if (minb == 4) k_shade<4, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
-		else k_shade<2, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
+		k_shade<4, 1><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+		if (minb == 3) k_shade<3, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+		else if (minb == 4) k_shade<4, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+		else k_shade<2, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
 		return;
 	}
-	if (minb == 3) k_shade<3, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
-	else if (minb == 4) k_shade<4, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
-	else k_shade<2, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode);
+	if (minb == 3) k_shade<3, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+	else if (minb == 4) k_shade<4, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+	else k_shade<2, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
 }
 void crg_launch_dirsort(const WaveBuffers &wb, int nxt, int grid, cudaStream_t st) {
 	k_bucket<true><<<grid, 256, 0, st>>>(wb, nxt);

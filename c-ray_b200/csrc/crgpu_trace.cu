@@ -54,9 +54,10 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
 #define CRG_REFILL 16
 #define CRG_NODE_BURST 3
 #define CRG_STAGE_MIN_RAYS 65536u
+#define CRG_DEFER_DEFAULT 0
 #define CRG_MAX_STEPS 8000000u   /* > 30x the node count of any scene that fits the 2^23-node address space we support */
 
-template <bool COUNT, int MINB, bool DEFER>
+template <bool COUNT, int MINB, int DEFER>
 __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb, int cur, int refill, int burst, int sorted, int inst_min) {
 	const unsigned n = wb.counts[cur];
 	const unsigned lane = threadIdx.x & 31u;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 	const float4 *__restrict__ stB = wb.stB[cur];
 	TraceCounters tc = { 0u, 0u, 0u, 0u };
 	__shared__ unsigned s_hist[256];
+	__shared__ CoopScratch s_coop[DEFER == 2 ? 8 : 1];   /* one per warp (blockDim.x == 256) */
 	s_hist[threadIdx.x] = 0u;            /* blockDim.x == 256 */
 	/* K3 + K4b of the previous bounce are done with the direction-bin counters: clear them for this bounce's K3 */
 	if (blockIdx.x == 0) { wb.hist[512 + threadIdx.x] = 0u; wb.hist[768 + threadIdx.x] = 0u; }
@@ -133,10 +135,11 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 		for (int k = 0; k < burst; ++k) {
 			const bool wn = busy && tr.wants_node();
 			if (!__any_sync(0xffffffffu, wn)) break;
-			if (wn) { tr.template node_step<DEFER>(sc, &tc); ++steps; }
+			if (wn) { tr.template node_step<DEFER != 0>(sc, &tc); ++steps; }
 		}
 		/* Phase T (DEFER): the triangles of every lane that reached a leaf during the burst, together */
-		if (DEFER && busy && tr.wants_leaf()) tr.leaf_step(sc, &tc);
+		if (DEFER == 2) cr_coop_leaves<COUNT>(tr, busy && tr.wants_leaf(), sc, s_coop[threadIdx.x >> 5], lane, &tc);   /* dealt over the warp */
+		else if (DEFER == 1 && busy && tr.wants_leaf()) tr.leaf_step(sc, &tc);
 		/* Phase I: one pending instance (ray transform + sphere test, or entry into a mesh BVH).  ncu (profiles/r01: 19.8% of K2's
 		 * warp instructions ran with fewer than 2 active lanes, almost all of them here): lanes reach a top-level leaf at different
 		 * iterations, so running this ~100-instruction block whenever ANY lane wants it means running it for one lane.  Lanes
@@ -197,7 +200,7 @@ void crg_launch_generate(const DevScene &sc, const WaveBuffers &wb, const TileDe
 #ifndef CRG_MAX_DEVICES
 #define CRG_MAX_DEVICES 64
 #endif
-template <bool COUNT, int MINB, bool DEFER>
+template <bool COUNT, int MINB, int DEFER>
 static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int cur, bool sorted, cudaStream_t st) {
 	/* launch shape per DEVICE: the host mirror drives several GPUs from one process (one thread each), and both the
 	 * occupancy answer and the opt-in shared-memory attribute belong to a device, not to the process */
@@ -230,15 +233,21 @@ static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int 
 void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, bool sorted, int grid, cudaStream_t st) {
 	(void)grid;
 	static const int minb = [] { const char *e = getenv("CRGPU_TRACE_MINB"); const int v = e ? atoi(e) : 3; return v >= 2 && v <= 4 ? v : 3; }();
-	static const int defer = [] { const char *e = getenv("CRGPU_TRACE_DEFER"); return e ? atoi(e) : 0; }();
-	if (count) { if (defer) launch_trace_variant<true, 3, true>(sc, wb, cur, sorted, st); else launch_trace_variant<true, 3, false>(sc, wb, cur, sorted, st); return; }
-	if (defer) {
-		if (minb == 4) launch_trace_variant<false, 4, true>(sc, wb, cur, sorted, st);
-		else if (minb == 2) launch_trace_variant<false, 2, true>(sc, wb, cur, sorted, st);
-		else launch_trace_variant<false, 3, true>(sc, wb, cur, sorted, st);
-	} else {
-		if (minb == 4) launch_trace_variant<false, 4, false>(sc, wb, cur, sorted, st);
-		else if (minb == 2) launch_trace_variant<false, 2, false>(sc, wb, cur, sorted, st);
-		else launch_trace_variant<false, 3, false>(sc, wb, cur, sorted, st);
+	/* CRGPU_TRACE_DEFER: 0 = triangles tested inside the node step, 1 = lanes wait and test their own leaf after the burst,
+	 * 2 = lanes wait and the warp deals the (ray, triangle) pairs over its 32 lanes (cr_coop_leaves) */
+	static const int defer = [] { const char *e = getenv("CRGPU_TRACE_DEFER"); const int v = e ? atoi(e) : CRG_DEFER_DEFAULT; return v >= 0 && v <= 2 ? v : CRG_DEFER_DEFAULT; }();
+	if (count) {
+		if (defer == 2) launch_trace_variant<true, 3, 2>(sc, wb, cur, sorted, st);
+		else if (defer == 1) launch_trace_variant<true, 3, 1>(sc, wb, cur, sorted, st);
+		else launch_trace_variant<true, 3, 0>(sc, wb, cur, sorted, st);
+		return;
 	}
+#define CRG_TRACE_DISPATCH(D) do { \
+		if (minb == 4) launch_trace_variant<false, 4, D>(sc, wb, cur, sorted, st); \
+		else if (minb == 2) launch_trace_variant<false, 2, D>(sc, wb, cur, sorted, st); \
+		else launch_trace_variant<false, 3, D>(sc, wb, cur, sorted, st); } while (0)
+	if (defer == 2) CRG_TRACE_DISPATCH(2);
+	else if (defer == 1) CRG_TRACE_DISPATCH(1);
+	else CRG_TRACE_DISPATCH(0);
+#undef CRG_TRACE_DISPATCH
 }

@@ -398,6 +398,81 @@ struct Traversal {
 	}
 };
 
+/* ---- cooperative leaf phase (K2, DEFER == 2) ------------------------------------------------------------------------------------
+ * ncu (profiles/r02): a quarter of K2's warp instructions are Möller–Trumbore tests executed with ~2 active lanes — at any step only
+ * one or two lanes of a warp stand at a leaf, and the warp then runs the per-lane triangle loop max(leaf size) times for them.
+ * Here the lanes that reached a leaf WAIT (Traversal::leafN, as in DEFER == 1) and, after the node burst, the warp deals all their
+ * (ray, triangle) pairs out over its 32 lanes: one pass of the triangle code tests up to 32 pairs of up to 32 different rays.
+ * The ray of a pair is read from its owner lane with shuffles; candidates go back through 3 x 32 floats of shared memory per warp and
+ * every owner takes its winner IN LEAF ORDER with the reference's strict `t < distance` (poly.c:48, bvh.c:455-459: the first of equal
+ * distances wins), so hit records stay bit-identical.  Must be called by all 32 lanes of the warp (convergent). */
+struct CoopScratch { float t[32], u[32], v[32]; unsigned owner[32]; };
+
+template <bool COUNT>
+CRD void cr_coop_leaves(Traversal<COUNT> &tr, bool has, const DevScene &sc, CoopScratch &cs, unsigned lane, TraceCounters *ctr) {
+	const unsigned FULL = 0xffffffffu;
+	unsigned pending = __ballot_sync(FULL, has);
+	while (pending) {
+		const unsigned nA = tr.leafN & 0xffffu, nB = tr.leafN >> 16;
+		unsigned cnt = has ? nA + nB : 0u;
+		if (cnt > 32u) { tr.leaf_step(sc, ctr); has = false; cnt = 0u; }      /* an oversized leaf pair: the lane's own loop (rare) */
+		unsigned incl = cnt;
+#pragma unroll
+		for (unsigned dlt = 1u; dlt < 32u; dlt <<= 1) { const unsigned x = __shfl_up_sync(FULL, incl, dlt); if (lane >= dlt) incl += x; }
+		const bool fits = has && incl <= 32u;                 /* incl is non-decreasing over lanes: the lanes that fit form a prefix */
+		const unsigned excl = incl - cnt;
+		const unsigned startMask = __reduce_or_sync(FULL, fits ? (1u << (excl & 31u)) : 0u);
+		const unsigned tot = __reduce_max_sync(FULL, fits ? incl : 0u);
+		if (fits) cs.owner[excl & 31u] = lane;
+		__syncwarp();
+		/* pair `lane` of this round: owner = the lane whose segment [excl, incl) holds it */
+		unsigned seg = 0u, ow = lane;
+		if (lane < tot) { seg = 31u - (unsigned)__clz((int)(startMask & (0xffffffffu >> (31u - lane)))); ow = cs.owner[seg]; }
+		const float ox = __shfl_sync(FULL, tr.o.x, ow), oy = __shfl_sync(FULL, tr.o.y, ow), oz = __shfl_sync(FULL, tr.o.z, ow);
+		const float dx = __shfl_sync(FULL, tr.d.x, ow), dy = __shfl_sync(FULL, tr.d.y, ow), dz = __shfl_sync(FULL, tr.d.z, ow);
+		const unsigned lA = __shfl_sync(FULL, tr.leafA, ow), lB = __shfl_sync(FULL, tr.leafB, ow), lN = __shfl_sync(FULL, tr.leafN, ow);
+		const unsigned sb = __shfl_sync(FULL, tr.slotBase, ow);
+		if (lane < tot) {
+			const unsigned k = lane - seg, onA = lN & 0xffffu;
+			const unsigned slot = k < onA ? lA + k : lB + (k - onA);
+			const float4 *t4 = reinterpret_cast<const float4 *>(sc.tris + sb + slot);
+			const float4 a = __ldg(t4 + 0), b = __ldg(t4 + 1), c4 = __ldg(t4 + 2);
+			if (COUNT) ctr->tris++;
+			const v3 o = v3make(ox, oy, oz), d = v3make(dx, dy, dz);
+			const v3 v0 = v3make(a.x, a.y, a.z), e1 = v3make(a.w, b.x, b.y), e2 = v3make(b.z, b.w, c4.x);
+			const v3 n = v3make(c4.y, c4.z, c4.w);
+			const v3 c = v3sub(v0, o);
+			const v3 r = v3cross(d, c);
+			const float invDet = cr_div(1.0f, v3dot(n, d));
+			const float u = v3dot(r, e2) * invDet;
+			const float v = v3dot(r, e1) * invDet;
+			float tt = __int_as_float(0x7f800000);              /* +inf: never `< distance` */
+			if (u >= 0.0f && v >= 0.0f && u + v <= 1.0f) {
+				const float t = v3dot(n, c) * invDet;
+				if (t >= 0.0f) tt = t;
+			}
+			cs.t[lane] = tt; cs.u[lane] = u; cs.v[lane] = v;
+		}
+		__syncwarp();
+		if (fits) {
+			float bt = tr.best.t;
+			int kb = -1;
+			for (unsigned k = 0u; k < cnt; ++k) { const float x = cs.t[excl + k]; if (x < bt) { bt = x; kb = (int)k; } }
+			if (kb >= 0) {
+				const unsigned k = (unsigned)kb;
+				tr.best.t = bt; tr.best.u = cs.u[excl + k]; tr.best.v = cs.v[excl + k];
+				tr.best.prim = tr.slotBase + (k < nA ? tr.leafA + k : tr.leafB + (k - nA));
+				tr.instHit = true;
+			}
+			tr.leafN = 0u;
+			tr.finish_bottom(sc);
+			has = false;
+		}
+		__syncwarp();
+		pending = __ballot_sync(FULL, has);
+	}
+}
+
 template <bool COUNT>
 CRD Hit cr_closest_hit(const DevScene &sc, v3 wo, v3 wd, TraceCounters *ctr) {
 	uint32_t stack[2 * CRG_MAX_STACK + 2];
