@@ -88,3 +88,49 @@ def free(scene):
     if scene.owner:
         _libc.free(scene.owner)
         scene.owner = None
+
+
+def prim_boxes(vertices, polys):
+    """(bboxes n x 6, centers n x 3) of a mesh's triangles exactly as the loader computes them (cr_sceneload.c poly_bbox <- reference
+    bvh.c:283-291): the min/max MACROS (a < b ? a : b — ties return the second operand, which decides the sign of a zero) and the
+    centre (v0 + v1 + v2) * (1/3) in fp32."""
+    V = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    v0, v1, v2 = V[polys["v"][:, 0]], V[polys["v"][:, 1]], V[polys["v"][:, 2]]
+    mn = lambda a, b: np.where(a < b, a, b)
+    mx = lambda a, b: np.where(a > b, a, b)
+    bb = np.concatenate([mn(v0, mn(v1, v2)), mx(v0, mx(v1, v2))], axis=1).astype(np.float32)
+    ct = ((v0 + v1).astype(np.float32) + v2).astype(np.float32) * np.float32(1.0 / 3.0)
+    return np.ascontiguousarray(bb), np.ascontiguousarray(ct.astype(np.float32))
+
+
+def _build(fn, bboxes, centers, *extra):
+    bb = np.ascontiguousarray(bboxes, dtype=np.float32).reshape(-1, 6)
+    ct = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1, 3)
+    n = len(bb)
+    nodes = np.zeros(max(2 * n, 1), dtype=BVH_NODE)
+    prims = np.zeros(max(n, 1), dtype=np.int32)
+    cnt = C.c_uint32(0)
+    rc = fn(bb.ctypes.data_as(C.c_void_p), ct.ctypes.data_as(C.c_void_p), C.c_uint32(n), *extra,
+            nodes.ctypes.data_as(C.c_void_p), C.byref(cnt), prims.ctypes.data_as(C.c_void_p))
+    return rc, nodes[:cnt.value].copy(), prims[:n].copy()
+
+
+def build_bvh(bboxes, centers):
+    """crloader_build_bvh: the host binned-SAH builder on its own -> (nodes BVH_NODE[], prims int32[])."""
+    L = loader()
+    L.crloader_build_bvh.restype = C.c_int
+    rc, nodes, prims = _build(L.crloader_build_bvh, bboxes, centers)
+    if rc != 0:
+        raise RuntimeError("crloader_build_bvh failed")
+    return nodes, prims
+
+
+def build_bvh_gpu(bboxes, centers, device=0):
+    """crgpu_bvh_build: the same tree built on the device."""
+    import crgpu
+    G = crgpu.lib()
+    G.crgpu_bvh_build.restype = C.c_int
+    rc, nodes, prims = _build(G.crgpu_bvh_build, bboxes, centers, C.c_int(device))
+    if rc != 0:
+        raise crgpu.CrgpuError(f"crgpu_bvh_build failed ({rc}): " + G.crgpu_last_error().decode(errors="replace"))
+    return nodes, prims

@@ -30,6 +30,14 @@ static int fail(int code, const char *fmt, ...) {
 	va_end(vl);
 	return code;
 }
+/* the same for the other translation units of libcrgpu.so (crgpu_bvh_build.cu) */
+int crg_fail(int code, const char *fmt, ...) {
+	va_list vl;
+	va_start(vl, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, vl);
+	va_end(vl);
+	return code;
+}
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(CRGPU_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 extern "C" const char *crgpu_last_error(void) { return g_err; }

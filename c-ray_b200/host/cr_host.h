@@ -135,6 +135,10 @@ float *crhostRenderBuffer(struct renderer *r);
 double crhostRenderSeconds(const struct renderer *r);
 unsigned long long crhostTotalRays(const struct renderer *r);
 void crhostConfigure(struct renderer *r, int gpus, unsigned tileWidth, unsigned tileHeight, int quiet);
+/* build the BVHs of the scenes loaded after this call on CUDA device `device` (crgpu_bvh_build) when they have at
+ * least min_prims primitives; on == 0 goes back to the host builder.  Same tree either way.  Also switched on by the environment
+ * variable CRAY_GPU_BVH=<min_prims> (read by loadSceneFile / loadSceneBuf). */
+void crhostUseGpuBvh(int on, int device, unsigned min_prims);
 void crhostImageSize(const struct renderer *r, unsigned *w, unsigned *h, int *samples, int *bounces);
 void *crhostComm(struct renderer *r);
 const void *crhostPrepared(struct renderer *r);

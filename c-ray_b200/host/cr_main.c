@@ -16,7 +16,7 @@ static int parse_dims(const char *s, int *w, int *h) { return s && sscanf(s, "%d
 
 int main(int argc, char **argv) {
 	if (argc < 2) {
-		fprintf(stderr, "usage: %s scene.json|scene.crscene [-d WxH] [-s samples] [-b bounces] [-t tileWxtileH] [-j gpus] [-o out.png|out.bmp] [--dump-f32 file] [-q]\n", argv[0]);
+		fprintf(stderr, "usage: %s scene.json|scene.crscene [-d WxH] [-s samples] [-b bounces] [-t tileWxtileH] [-j gpus] [-o out.png|out.bmp] [--dump-f32 file] [--gpu-bvh] [-q]\n", argv[0]);
 		return 1;
 	}
 	int W = 0, H = 0, spp = 0, bounces = 0, tw = 0, th = 0, gpus = 1, quiet = 0;
@@ -30,6 +30,7 @@ int main(int argc, char **argv) {
 		else if (!strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
 		else if (!strcmp(argv[i], "--dump-f32") && i + 1 < argc) dump = argv[++i];
 		else if (!strcmp(argv[i], "-q")) quiet = 1;
+		else if (!strcmp(argv[i], "--gpu-bvh")) crhostUseGpuBvh(1, 0, 1024);      /* BVHs of >= 1024 primitives built on device 0 */
 		else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
 	}
 	struct renderer *r = newRenderer();

@@ -81,10 +81,30 @@ struct renderer *newRenderer(void) {                              /* renderer.c:
 	return r;
 }
 
+/* ---- the loader's BVH builds on the device ------------------------------------------------------------------------ */
+static int g_bvh_device;
+static int gpu_bvh_builder(const float *bb, const float *ct, uint32_t n, struct crs_bvh_node *nodes, uint32_t *count, int32_t *prims) {
+	const int rc = crgpu_bvh_build(bb, ct, n, g_bvh_device, nodes, count, prims);
+	if (rc != CRGPU_OK) fprintf(stderr, "cray_b200: device BVH build failed (%s); building on the host\n", crgpu_last_error());
+	return rc;
+}
+void crhostUseGpuBvh(int on, int device, unsigned min_prims) {
+	g_bvh_device = device;
+	crloader_set_bvh_builder(on ? gpu_bvh_builder : NULL, min_prims);
+}
+static void gpu_bvh_from_env(void) {
+	static int done;
+	if (done) return;
+	done = 1;
+	const char *e = getenv("CRAY_GPU_BVH");
+	if (e && *e) crhostUseGpuBvh(1, 0, (unsigned)strtoul(e, NULL, 10));
+}
+
 static void drop_prepared(struct renderer *r) { if (r->prepared) { crgpu_prepared_free(r->prepared); r->prepared = NULL; } }
 
 int loadSceneFile(struct renderer *r, const char *path, int width, int height, int samples, int bounces) {
 	size_t n = strlen(path);
+	gpu_bvh_from_env();
 	drop_prepared(r);
 	if (n > 5 && !strcasecmp(path + n - 5, ".json")) {
 		/* a c-ray JSON scene: parse + build both BVH levels on the host (libcrloader.so, include/crloader.h) */
@@ -98,6 +118,7 @@ int loadSceneFile(struct renderer *r, const char *path, int width, int height, i
 
 int loadSceneBuf(struct renderer *r, const char *json, const char *assetPath, struct crloader_output *output,
 				 int width, int height, int samples, int bounces) {
+	gpu_bvh_from_env();
 	drop_prepared(r);
 	if (crloader_load_json_buf(&r->scene, json, assetPath, output) != 0) {
 		fprintf(stderr, "cray_b200: %s\n", crloader_last_error());

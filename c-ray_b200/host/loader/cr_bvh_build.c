@@ -11,6 +11,7 @@
  * built by several threads with a layout pass that restores the serial node numbering.
  */
 #include "cr_loader_int.h"
+#include "../../../include/crloader.h"
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
@@ -252,10 +253,39 @@ static void layout(const struct top *tops, const struct task *tasks, int t, unsi
 #define PARALLEL_MIN_PRIMS 8192u     /* below this a single serial build is faster than starting threads */
 #define TASK_MIN_PRIMS     2048u
 
+/* an alternative builder for large inputs (crloader_set_bvh_builder): the device build of SURVEY 8(f1), wired in by libcrhost */
+static crloader_bvh_builder g_builder;
+static uint32_t g_builder_min;
+void crloader_set_bvh_builder(crloader_bvh_builder fn, uint32_t min_prims) { g_builder = fn; g_builder_min = min_prims; }
+
+static int build_with_hook(void *user, crl_bbox_fn fn, unsigned count,
+                           struct crs_bvh_node **out_nodes, uint32_t *out_count, int32_t **out_prims) {
+	float *bb = malloc(sizeof(float) * 6 * (size_t)count), *ct = malloc(sizeof(float) * 3 * (size_t)count);
+	struct crs_bvh_node *nodes = calloc((size_t)2 * count, sizeof(*nodes));
+	int32_t *prims = malloc(sizeof(int32_t) * (size_t)count);
+	int rc = -1;
+	if (bb && ct && nodes && prims) {
+		for (unsigned i = 0; i < count; ++i) {
+			bbox3 b; vec3 c;
+			fn(user, i, &b, &c);
+			bb[6 * (size_t)i] = b.min.x; bb[6 * (size_t)i + 1] = b.min.y; bb[6 * (size_t)i + 2] = b.min.z;
+			bb[6 * (size_t)i + 3] = b.max.x; bb[6 * (size_t)i + 4] = b.max.y; bb[6 * (size_t)i + 5] = b.max.z;
+			ct[3 * (size_t)i] = c.x; ct[3 * (size_t)i + 1] = c.y; ct[3 * (size_t)i + 2] = c.z;
+		}
+		uint32_t n = 0;
+		rc = g_builder(bb, ct, count, nodes, &n, prims);
+		if (rc == 0 && n >= 1) { *out_nodes = realloc(nodes, sizeof(*nodes) * n); *out_count = n; *out_prims = prims; nodes = NULL; prims = NULL; }
+		else rc = -1;
+	}
+	free(bb); free(ct); free(nodes); free(prims);
+	return rc;
+}
+
 int crl_build_bvh(void *user, crl_bbox_fn fn, unsigned count,
                   struct crs_bvh_node **out_nodes, uint32_t *out_count, int32_t **out_prims) {
 	*out_nodes = NULL; *out_count = 0; *out_prims = NULL;
 	if (count < 1) return 0;
+	if (g_builder && count >= g_builder_min && build_with_hook(user, fn, count, out_nodes, out_count, out_prims) == 0) return 0;
 	vec3 *centers = malloc(sizeof(vec3) * count);
 	bbox3 *bboxes = malloc(sizeof(bbox3) * count);
 	int32_t *prims = malloc(sizeof(int32_t) * count);
@@ -345,4 +375,35 @@ int crl_build_bvh(void *user, crl_bbox_fn fn, unsigned count,
 	*out_count = node_count;
 	*out_prims = prims;
 	return 0;
+}
+
+/* ---- the builder on its own (include/crloader.h) ---------------------------------------------------------------------------------- */
+struct array_user { const float *bb, *ct; };
+static void array_bbox(void *user, unsigned i, bbox3 *bbox, vec3 *center) {
+	const struct array_user *u = user;
+	bbox->min = (vec3){ u->bb[6 * (size_t)i], u->bb[6 * (size_t)i + 1], u->bb[6 * (size_t)i + 2] };
+	bbox->max = (vec3){ u->bb[6 * (size_t)i + 3], u->bb[6 * (size_t)i + 4], u->bb[6 * (size_t)i + 5] };
+	*center = (vec3){ u->ct[3 * (size_t)i], u->ct[3 * (size_t)i + 1], u->ct[3 * (size_t)i + 2] };
+}
+
+int crloader_build_bvh(const float *bboxes, const float *centers, uint32_t n,
+                       struct crs_bvh_node *nodes_out, uint32_t *node_count_out, int32_t *prims_out) {
+	if (!node_count_out || (n && (!bboxes || !centers || !nodes_out || !prims_out))) return -1;
+	*node_count_out = 0;
+	if (n == 0) return 0;
+	struct array_user u = { bboxes, centers };
+	struct crs_bvh_node *nodes = NULL;
+	int32_t *prims = NULL;
+	uint32_t cnt = 0;
+	const crloader_bvh_builder saved = g_builder;
+	g_builder = NULL;                                  /* always the host algorithm */
+	const int rc = crl_build_bvh(&u, array_bbox, n, &nodes, &cnt, &prims);
+	g_builder = saved;
+	if (rc == 0) {
+		memcpy(nodes_out, nodes, sizeof(*nodes) * cnt);
+		memcpy(prims_out, prims, sizeof(int32_t) * n);
+		*node_count_out = cnt;
+	}
+	free(nodes); free(prims);
+	return rc;
 }

@@ -134,6 +134,16 @@ int crgpu_scene_info(crgpu_scene *s, int *device, int *width, int *height);
  * (x, y, pass) triples, in the 160-byte record layout of oracle/ref_harness.c `struct hit_kat`. */
 int crgpu_trace_kat(crgpu_scene *s, const int32_t *xyp, int count, void *records_out);
 
+/* the reference's binned-SAH BVH build (reference src/accelerators/bvh.c:96-296: partitionPrimitives,
+ * buildBvhRecursive, buildBvhGeneric) on device `device`, level-synchronous (c-ray_b200/csrc/crgpu_bvh_build.cu).  Produces the
+ * SAME tree as the reference and as the host builder (crloader_build_bvh): node order, leaf ranges, primitive order, bounds.
+ *   bboxes   n x 6 floats: min.x min.y min.z max.x max.y max.z of every primitive (what getBBoxAndCenter returns, bvh.c:283-291)
+ *   centers  n x 3 floats
+ *   nodes_out  room for 2n-1 nodes;  prims_out  n indices (primIndices);  *node_count_out  nodes written
+ * n == 0 writes nothing (an empty BVH, bvh.c:251).  At most 4,194,304 primitives per call. */
+int crgpu_bvh_build(const float *bboxes, const float *centers, uint32_t n, int device,
+                    struct crs_bvh_node *nodes_out, uint32_t *node_count_out, int32_t *prims_out);
+
 #ifdef __cplusplus
 }
 #endif

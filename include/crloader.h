@@ -35,6 +35,19 @@ struct crloader_output {
 int crloader_load_json_buf(struct crs_scene *out, const char *json_text, const char *asset_path, struct crloader_output *output);
 const char *crloader_last_error(void);
 
+/* The BVH builder on its own (reference src/accelerators/bvh.c:245-296 buildBvhGeneric): n primitives given by their boxes
+ * (n x 6 floats: min.xyz, max.xyz) and centers (n x 3); nodes_out has room for 2n-1 nodes, prims_out for n indices.
+ * Host counterpart of crgpu_bvh_build (crgpu.h), same outputs bit for bit.  0 on success. */
+int crloader_build_bvh(const float *bboxes, const float *centers, uint32_t n,
+                       struct crs_bvh_node *nodes_out, uint32_t *node_count_out, int32_t *prims_out);
+
+/* Route the BVH builds of crloader_load_json* through another builder with crloader_build_bvh's signature (e.g. a wrapper of
+ * crgpu_bvh_build) for inputs of at least `min_prims` primitives; NULL restores the host builder.  A builder that returns
+ * non-zero falls back to the host builder for that BVH.  Process-wide; set it before loading. */
+typedef int (*crloader_bvh_builder)(const float *bboxes, const float *centers, uint32_t n,
+                                    struct crs_bvh_node *nodes_out, uint32_t *node_count_out, int32_t *prims_out);
+void crloader_set_bvh_builder(crloader_bvh_builder fn, uint32_t min_prims);
+
 #ifdef __cplusplus
 }
 #endif
