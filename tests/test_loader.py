@@ -115,7 +115,7 @@ def test_loader_exports_declared_symbols():
     import re
     text = open(os.path.join(ROOT, "include", "crloader.h")).read()
     names = sorted(set(re.findall(r"\b(crloader_\w+)\s*\(", text)))
-    assert names == ["crloader_last_error", "crloader_load_json", "crloader_load_json_buf"]
+    assert names == ["crloader_build_bvh", "crloader_last_error", "crloader_load_json", "crloader_load_json_buf", "crloader_set_bvh_builder"]
     L = C.CDLL(crscene.LOADER_PATH)
     for n in names:
         getattr(L, n)
