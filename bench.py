@@ -3,8 +3,8 @@
 
 A "step" is one complete render of the workload frame: default = configs[1] of BASELINE.json,
 input/hdr.json at 1920x1080, 1000 spp, 32 bounces; --workload refraction | venus | hdr8k are configs[2..4].
-The tile queue of the host C dispatcher (quantizeImage order) is dealt out to the ranks by queue position
-(k % world, cr_renderer.c takeRankTiles); the frame is fixed, so this is STRONG scaling.  With N>1 the fp32
+The tile grid of the host C dispatcher (quantizeImage) is dealt out to the ranks by a spatial interleave
+((tx + 5 ty) % world, cr_renderer.c takeRankTiles); the frame is fixed, so this is STRONG scaling.  With N>1 the fp32
 framebuffer tiles are gathered on rank 0 over NCCL (libcrgpu_nccl.so) inside the timed region.
 
   value      Mray/s, whole job, scene + framebuffer resident in HBM, device-timed (CUDA events), max over ranks;
@@ -257,6 +257,12 @@ def main():
         reference_arm(args, w, rank)
         return
 
+    # rank 0 prints ONE JSON line on stdout and nothing else: NCCL announces "NCCL version ..." on fd 1 when the first communicator is
+    # created (torch's and libcrgpu_nccl's), so fd 1 points at stderr for the whole run and the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import zlib
     import numpy as np
     import torch
@@ -461,7 +467,7 @@ def main():
                 "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "bundled scene " + scene_src + " (no synthetic tensors on this path)",
                 "config": {"workload": f"input/{w['scene']}.json {W}x{H} {spp} spp {bounces} bounces", "name": args.workload, "tile": tile,
-                           "parallelism": f"tile-sharded x{world} (queue position % world), one NCCL gather per frame" if world > 1 else "1 GPU",
+                           "parallelism": f"tile-sharded x{world} (tile (tx + 5 ty) % world), one NCCL gather per frame" if world > 1 else "1 GPU",
                            "l2": "wavefront state (GBs per step) streams through the 126 MB L2: inputs larger than L2, no explicit flush"},
                 "msample_per_s": round(msample, 2), "rays_per_sample": round(rays / paths, 4), "rank_ms_per_step": rank_ms if world > 1 else None,
                 "e2e": {"value": round(e2e_value, 2), "unit": "Mray/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * W * 3 * 4 + H * W * 3,
@@ -478,7 +484,8 @@ def main():
             ingest = scene_ingest(w["scene"])
             if ingest:
                 line["scene_ingest"] = ingest
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -51,6 +51,8 @@ def lib():
         L.crhostSetRank.argtypes = [P, C.c_int, C.c_int]
         L.crhostResetQueue.argtypes = [P]
         L.takeRankTiles.argtypes = [P, P, P]
+        L.crhostTileOwners.argtypes = [P, C.c_int, P]
+        L.crhostTileOwners.restype = None
         _lib = L
     return _lib
 
@@ -111,7 +113,8 @@ class Renderer:
         L.crhostResetQueue(self.r)
         got = L.takeRankTiles(self.r, rects.ctypes.data, nums.ctypes.data)
         L.crhostResetQueue(self.r)
-        owner = (np.arange(n, dtype=np.int32) % world).astype(np.int32)
+        owner = np.zeros(n, dtype=np.int32)
+        L.crhostTileOwners(self.r, world, owner.ctypes.data)
         return rects[:got].copy(), owner, every
 
     def comm(self):

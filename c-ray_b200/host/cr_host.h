@@ -146,6 +146,7 @@ int crhostTileCount(const struct renderer *r);
 void crhostSetRank(struct renderer *r, int rank, int world);
 void crhostResetQueue(struct renderer *r);
 int takeRankTiles(struct renderer *r, int *rects, int *nums);
+void crhostTileOwners(struct renderer *r, int world, int *owners);   /* owner rank of every tile, in queue order */
 
 /* worker entry point with the signature of renderThread (void *(*)(void *)) */
 void *gpuRenderThread(void *arg);

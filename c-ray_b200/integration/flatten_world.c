@@ -23,6 +23,7 @@
 #include "datatypes/material.h"
 #include "accelerators/bvh.h"
 #include "nodes/bsdfnode.h"
+#include "nodes/vectornode.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -55,6 +56,7 @@ static int flat_tex(const struct texture *t) {
 
 static int flat_value(const struct valueNode *n);
 static int flat_color(const struct colorNode *n);
+static int flat_vector(const struct vectorNode *n);
 
 static int node_slot(const void *n) {
 	int idx = map_add(&g_nodes, n);
@@ -84,9 +86,15 @@ static int flat_color(const struct colorNode *n) {
 	} else if (crx_is_checker(n, &o)) {
 		int a = flat_color(o.in[0]), b = flat_color(o.in[1]), s = flat_value(o.in[2]);
 		node_fill(idx, &o, a, b, s);
-	} else if (crx_is_blackbody(n, &o)) {
+	} else if (crx_is_blackbody(n, &o) || crx_is_combine_value(n, &o)) {
 		int t = flat_value(o.in[0]);
 		node_fill(idx, &o, t, -1, -1);
+	} else if (crx_is_combine_rgb(n, &o)) {
+		int r = flat_value(o.in[0]), g = flat_value(o.in[1]), b = flat_value(o.in[2]);
+		node_fill(idx, &o, r, g, b);
+	} else if (crx_is_vectocolor(n, &o)) {
+		int v = flat_vector(o.in[0]);
+		node_fill(idx, &o, v, -1, -1);
 	} else {
 		fprintf(stderr, "flatten_world: color node type not exportable\n"); g_flat_error = 1; return -1;
 	}
@@ -104,8 +112,33 @@ static int flat_value(const struct valueNode *n) {
 	} else if (crx_is_grayscale(n, &o) || crx_is_alpha(n, &o)) {
 		int c = flat_color(o.in[0]);
 		node_fill(idx, &o, c, -1, -1);
+	} else if (crx_is_math(n, &o)) {
+		int a = flat_value(o.in[0]), b = flat_value(o.in[1]);
+		node_fill(idx, &o, a, b, -1);
+	} else if (crx_is_fresnel(n, &o)) {
+		int ior = flat_value(o.in[0]), nv = flat_vector(o.in[1]);
+		node_fill(idx, &o, ior, nv, -1);
+	} else if (crx_is_raylength(n, &o)) {
+		node_fill(idx, &o, -1, -1, -1);
 	} else {
 		fprintf(stderr, "flatten_world: value node type not exportable\n"); g_flat_error = 1; return -1;
+	}
+	return idx;
+}
+
+static int flat_vector(const struct vectorNode *n) {
+	if (!n) return -1;
+	int idx = map_find(&g_nodes, n);
+	if (idx >= 0) return idx;
+	struct crx_nodeinfo o;
+	idx = node_slot(n);
+	if (crx_is_constant_vector(n, &o) || crx_is_normal(n, &o)) {
+		node_fill(idx, &o, -1, -1, -1);
+	} else if (crx_is_vecmath(n, &o)) {
+		int a = flat_vector(o.in[0]), b = flat_vector(o.in[1]);
+		node_fill(idx, &o, a, b, -1);
+	} else {
+		fprintf(stderr, "flatten_world: vector node type not exportable\n"); g_flat_error = 1; return -1;
 	}
 	return idx;
 }

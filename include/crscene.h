@@ -44,11 +44,29 @@ enum crs_node_kind {
 	CRS_COLOR_CHECKER    = 34, /* in0=A in1=B in2=scale(value)                checker.c:31-54   */
 	CRS_COLOR_GRADIENT   = 35, /* f[0..3]=down f[4..7]=up                     gradient.c:40-45  */
 	CRS_COLOR_BLACKBODY  = 36, /* in0=temperature(value)                      blackbody.c:38-42 */
+	CRS_COLOR_VECTOCOLOR = 37, /* in0=vector -> (x, y, z, 0)                  converter/vectocolor.c:38-43 */
+	CRS_COLOR_COMBINE_VALUE = 38, /* in0=value -> (v, v, v, 1)                converter/combine.c:38-43 */
+	CRS_COLOR_COMBINE_RGB = 39, /* in0..2 = R, G, B values, alpha 1           converter/combinergb.c:44-53 */
 	/* value nodes */
 	CRS_VALUE_CONSTANT   = 64, /* f[0]                                        valuenode.c       */
 	CRS_VALUE_GRAYSCALE  = 65, /* in0=color                                   grayscale.c:40-43 */
-	CRS_VALUE_ALPHA      = 66  /* in0=color                                   alpha.c:38-41     */
+	CRS_VALUE_ALPHA      = 66, /* in0=color                                   alpha.c:38-41     */
+	/* the node types only the reference's C constructors can build (no JSON path) */
+	CRS_VALUE_MATH       = 67, /* in0=A in1=B (values), options = enum mathOp converter/math.c:44-97 */
+	CRS_VALUE_FRESNEL    = 68, /* in0=IOR(value) in1=normal(vector, never evaluated)  input/fresnel.c:43-55 */
+	CRS_VALUE_RAYLENGTH  = 69, /* hit distance                                input/raylength.c:36-40 */
+	/* vector nodes: struct vectorValue { v, c, f } — every consumer reads .v only */
+	CRS_VECTOR_CONSTANT  = 96, /* f[0..2]                                     vectornode.c:38-42 */
+	CRS_VECTOR_NORMAL    = 97, /* surface normal of the hit                   input/normal.c:36-40 */
+	CRS_VECTOR_VECMATH   = 98  /* in0=A in1=B (vectors), options = enum vecOp converter/vecmath.c:43-83 */
 };
+/* options of CRS_VALUE_MATH: enum mathOp in the reference's order (converter/math.h:11-27) */
+enum crs_math_op { CRS_MATH_ADD, CRS_MATH_SUBTRACT, CRS_MATH_MULTIPLY, CRS_MATH_DIVIDE, CRS_MATH_POWER, CRS_MATH_LOG, CRS_MATH_SQRT,
+                   CRS_MATH_ABS, CRS_MATH_MIN, CRS_MATH_MAX, CRS_MATH_SINE, CRS_MATH_COSINE, CRS_MATH_TANGENT, CRS_MATH_TO_RADIANS,
+                   CRS_MATH_TO_DEGREES, CRS_MATH_OP_COUNT };
+/* options of CRS_VECTOR_VECMATH: enum vecOp (converter/vecmath.h:11-22); DOT and LENGTH produce .f and leave .v = (0,0,0) */
+enum crs_vec_op { CRS_VEC_ADD, CRS_VEC_SUBTRACT, CRS_VEC_MULTIPLY, CRS_VEC_AVERAGE, CRS_VEC_DOT, CRS_VEC_CROSS, CRS_VEC_NORMALIZE,
+                  CRS_VEC_REFLECT, CRS_VEC_LENGTH, CRS_VEC_ABS, CRS_VEC_OP_COUNT };
 
 /* image node options: reference src/nodes/textures/image.h */
 #define CRS_IMG_SRGB_TRANSFORM 0x01u

@@ -486,6 +486,33 @@ static col texture_get(const struct crs_scene *s, const struct crs_texture *t, f
 
 /* ---- nodes ------------------------------------------------------------------------------------------------------------ */
 static float eval_value(const struct crs_scene *s, int node, const struct hit *rec);
+static inline float schlick(float cosine, float IOR);
+
+/* vector nodes (vectornode.c:38-42, input/normal.c:36-40, converter/vecmath.c:43-83): struct vectorValue's .v member; the ops that
+ * produce the scalar .f (dot, length) leave .v zero-initialised, and no node of the reference reads .f */
+static v3 eval_vector(const struct crs_scene *s, int node, const struct hit *rec) {
+	const struct crs_node *n = &s->nodes[node];
+	switch (n->kind) {
+	case CRS_VECTOR_CONSTANT: return (v3){ n->f[0], n->f[1], n->f[2] };
+	case CRS_VECTOR_NORMAL: return rec->n;
+	case CRS_VECTOR_VECMATH: {
+		const v3 a = eval_vector(s, n->in[0], rec);
+		const v3 b = eval_vector(s, n->in[1], rec);
+		switch (n->options) {
+		case CRS_VEC_ADD: return v3add(a, b);
+		case CRS_VEC_SUBTRACT: return v3sub(a, b);
+		case CRS_VEC_MULTIPLY: return (v3){ a.x * b.x, a.y * b.y, a.z * b.z };
+		case CRS_VEC_AVERAGE: return v3scale(v3add(a, b), 0.5f);
+		case CRS_VEC_CROSS: return v3cross(a, b);
+		case CRS_VEC_NORMALIZE: return v3norm(a);
+		case CRS_VEC_REFLECT: return v3reflect(a, b);
+		case CRS_VEC_ABS: return (v3){ fabsf(a.x), fabsf(a.y), fabsf(a.z) };
+		default: return (v3){ 0, 0, 0 };                     /* VecDot, VecLength: .f only */
+		}
+	}
+	default: return (v3){ 0, 0, 0 };
+	}
+}
 
 static col eval_color(const struct crs_scene *s, int node, const struct hit *rec) {
 	const struct crs_node *n = &s->nodes[node];
@@ -522,6 +549,20 @@ static col eval_color(const struct crs_scene *s, int node, const struct hit *rec
 	}
 	case CRS_COLOR_BLACKBODY:                                                         /* blackbody.c:38-42 */
 		return color_for_kelvin(eval_value(s, n->in[0], rec));
+	case CRS_COLOR_VECTOCOLOR: {                                                      /* vectocolor.c:38-43 */
+		const v3 v = eval_vector(s, n->in[0], rec);
+		return (col){ v.x, v.y, v.z, 0.0f };
+	}
+	case CRS_COLOR_COMBINE_VALUE: {                                                   /* combine.c:38-43 */
+		const float v = eval_value(s, n->in[0], rec);
+		return (col){ v, v, v, 1.0f };
+	}
+	case CRS_COLOR_COMBINE_RGB: {                                                     /* combinergb.c:44-53: R, G, B in this order */
+		const float r = eval_value(s, n->in[0], rec);
+		const float g = eval_value(s, n->in[1], rec);
+		const float b = eval_value(s, n->in[2], rec);
+		return (col){ r, g, b, 1.0f };
+	}
 	default:
 		return (col){ 0, 0, 0, 1 };
 	}
@@ -533,6 +574,37 @@ static float eval_value(const struct crs_scene *s, int node, const struct hit *r
 	case CRS_VALUE_CONSTANT: return n->f[0];
 	case CRS_VALUE_GRAYSCALE: return to_grayscale(eval_color(s, n->in[0], rec)).r;     /* grayscale.c:40-43 */
 	case CRS_VALUE_ALPHA: return eval_color(s, n->in[0], rec).a;                        /* alpha.c:38-41 */
+	case CRS_VALUE_MATH: {                                                              /* math.c:44-97 */
+		const float a = eval_value(s, n->in[0], rec);
+		const float b = eval_value(s, n->in[1], rec);
+		switch (n->options) {
+		case CRS_MATH_ADD: return a + b;
+		case CRS_MATH_SUBTRACT: return a - b;
+		case CRS_MATH_MULTIPLY: return a * b;
+		case CRS_MATH_DIVIDE: return a / b;
+		case CRS_MATH_POWER: return powf(a, b);
+		case CRS_MATH_LOG: return log10f(a);
+		case CRS_MATH_SQRT: return sqrtf(a);
+		case CRS_MATH_ABS: return fabsf(a);
+		case CRS_MATH_MIN: return MIN_(a, b);
+		case CRS_MATH_MAX: return MAX_(a, b);
+		case CRS_MATH_SINE: return sinf(a);
+		case CRS_MATH_COSINE: return cosf(a);
+		case CRS_MATH_TANGENT: return tanf(a);
+		case CRS_MATH_TO_RADIANS: return (a * PI) / 180.0f;                             /* transforms.c:18-20 */
+		case CRS_MATH_TO_DEGREES: return a * (180.0f / PI);                             /* transforms.c:22-24 */
+		default: return 0.0f;
+		}
+	}
+	case CRS_VALUE_FRESNEL: {                                                           /* fresnel.c:43-55: IOR is evaluated twice */
+		const float IOR = eval_value(s, n->in[0], rec);
+		float cosine;
+		const float dn = v3dot(rec->incident.d, rec->n);
+		if (dn > 0.0f) cosine = IOR * v3dot(rec->incident.d, rec->n) / v3len(rec->incident.d);
+		else cosine = -(v3dot(rec->incident.d, rec->n) / v3len(rec->incident.d));
+		return schlick(cosine, eval_value(s, n->in[0], rec));
+	}
+	case CRS_VALUE_RAYLENGTH: return rec->dist;                                         /* raylength.c:36-40 */
 	default: return 0.0f;
 	}
 }

@@ -45,6 +45,52 @@ static double now_s(void) {
 	return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+/* ---- node types no JSON scene can reach (math, vecmath, fresnel, raylength, normal, vectocolor, combine) --------
+ * With CRAY_REF_F4 set, the materials of the loaded scene's spheres (and of its first mesh) are replaced by graphs built with the
+ * reference's own constructors, so that the golden fixture g_f4 pins every mathOp / vecOp against the unmodified eval() code. */
+#include "nodes/vectornode.h"
+#include "nodes/converter/math.h"
+#include "nodes/converter/vecmath.h"
+#include "nodes/converter/vectocolor.h"
+#include "nodes/converter/combine.h"
+#include "nodes/converter/combinergb.h"
+#include "nodes/converter/grayscale.h"
+#include "nodes/input/fresnel.h"
+#include "nodes/input/raylength.h"
+#include "nodes/input/normal.h"
+static void patch_f4_nodes(struct world *w) {
+#define CV(x) newConstantValue(w, (x))
+#define M2(a, b, op) newMath(w, (a), (b), (op))
+#define M1(a, op) newMath(w, (a), NULL, (op))
+#define VC(x, y, z) newConstantVector(w, (struct vector){ (x), (y), (z) })
+#define V2(a, b, op) newVecMath(w, (a), (b), (op))
+#define V1(a, op) newVecMath(w, (a), NULL, (op))
+	const struct vectorNode *N = newNormal(w);
+	const struct valueNode *RL = newRayLength(w);
+	const struct valueNode *FR = newFresnel(w, CV(1.45f), N);
+	const struct bsdfNode *g[8];
+	g[0] = newDiffuse(w, newCombineRGB(w, M1(M1(M2(RL, CV(3.0f), Multiply), Sine), Absolute), FR, M2(CV(0.8f), CV(0.25f), Subtract)));
+	g[1] = newMetal(w, newVecToColor(w, V1(N, VecAbs)), M2(FR, CV(0.3f), Multiply));
+	g[2] = newDiffuse(w, newCombineValue(w, M2(M2(M2(M1(M1(RL, Cosine), Absolute), CV(2.0f), Power), CV(0.1f), Max), CV(0.95f), Min)));
+	g[3] = newDiffuse(w, newCombineRGB(w, M2(M1(M1(M1(M2(RL, CV(0.5f), Multiply), Tangent), Absolute), SquareRoot), CV(1.0f), Min),
+										 M1(CV(40.0f), ToRadians), M1(CV(0.01f), ToDegrees)));
+	g[4] = newDiffuse(w, newVecToColor(w, V1(V1(V2(V2(N, VC(0.0f, 1.0f, 0.0f), VecCross), V2(N, VC(0.5f, 0.5f, 0.5f), VecMultiply), VecAdd), VecNormalize), VecAbs)));
+	g[5] = newDiffuse(w, newVecToColor(w, V1(V2(V2(N, VC(0.0f, 1.0f, 0.0f), VecReflect), V2(N, VC(0.2f, 0.1f, 0.3f), VecSubtract), VecAverage), VecAbs)));
+	g[6] = newDiffuse(w, newVecToColor(w, V2(V2(N, N, VecDot), V2(V1(N, VecLength), VC(0.3f, 0.6f, 0.9f), VecAdd), VecAdd)));
+	g[7] = newGlass(w, newCombineValue(w, CV(0.95f)), M1(CV(1.02f), Log), M2(CV(3.0f), CV(2.0f), Divide));
+	for (int i = 0; i < w->sphereCount && i < 8; ++i) w->spheres[i].material.bsdf = g[i];
+	if (w->meshCount > 0)
+		for (int m = 0; m < w->meshes[0].materialCount; ++m)
+			w->meshes[0].materials[m].bsdf = newDiffuse(w, newCombineRGB(w, M2(CV(0.2f), M2(FR, CV(0.5f), Multiply), Add), CV(0.4f),
+				newGrayscaleConverter(w, newVecToColor(w, V1(N, VecAbs)))));
+#undef CV
+#undef M2
+#undef M1
+#undef VC
+#undef V2
+#undef V1
+}
+
 /* ---- load through the reference's own API, with the CLI overrides of args.c:95-142 ------------- */
 static void load_scene(const char *json, int W, int H, int spp, int bounces, int threads, int tw, int th) {
 	char dims[64], tdims[64], sppstr[32], thr[32];
@@ -69,6 +115,7 @@ static void load_scene(const char *json, int W, int H, int spp, int bounces, int
 	if (crLoadSceneFromBuf(input) != 0) { fprintf(stderr, "ref_harness: scene load failed\n"); exit(3); }
 	free(input);
 	if (bounces > 0) g_renderer->prefs.bounces = bounces; /* no CLI flag for bounces (args.c:28-44) */
+	if (getenv("CRAY_REF_F4")) patch_f4_nodes(g_renderer->scene);
 }
 
 /* ---- flatten: c-ray_b200/integration/flatten_world.c (the reference-side integration code; linked into this harness) ---- */

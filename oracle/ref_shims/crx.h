@@ -12,7 +12,7 @@
 #include <stdbool.h>
 #include <stdint.h>
 
-struct bvh; struct bvhNode; struct bsdfNode; struct colorNode; struct valueNode; struct texture;
+struct bvh; struct bvhNode; struct bsdfNode; struct colorNode; struct valueNode; struct vectorNode; struct texture;
 
 struct crx_nodeinfo {
 	int kind;                 /* enum crs_node_kind */
@@ -48,3 +48,14 @@ bool crx_is_blackbody(const struct colorNode *n, struct crx_nodeinfo *o);
 bool crx_is_constant_value(const struct valueNode *n, struct crx_nodeinfo *o);
 bool crx_is_grayscale(const struct valueNode *n, struct crx_nodeinfo *o);
 bool crx_is_alpha(const struct valueNode *n, struct crx_nodeinfo *o);
+
+/* the node types without a JSON path */
+bool crx_is_vectocolor(const struct colorNode *n, struct crx_nodeinfo *o);
+bool crx_is_combine_value(const struct colorNode *n, struct crx_nodeinfo *o);
+bool crx_is_combine_rgb(const struct colorNode *n, struct crx_nodeinfo *o);
+bool crx_is_math(const struct valueNode *n, struct crx_nodeinfo *o);
+bool crx_is_fresnel(const struct valueNode *n, struct crx_nodeinfo *o);
+bool crx_is_raylength(const struct valueNode *n, struct crx_nodeinfo *o);
+bool crx_is_constant_vector(const struct vectorNode *n, struct crx_nodeinfo *o);
+bool crx_is_normal(const struct vectorNode *n, struct crx_nodeinfo *o);
+bool crx_is_vecmath(const struct vectorNode *n, struct crx_nodeinfo *o);
