@@ -7,8 +7,6 @@
 #include "crgpu_wave.cuh"
 #include "crgpu_scene.cuh"
 
-#define CRG_NODE_DEPTH 3
-#define CRG_ADD_STACK 4
 #define CRG_HITKAT_BYTES 160
 #define CRG_TAIL_FROM 6      /* first bounce at which the tail kernel may take over (it only does when <= 16384 rays are left) */
 
@@ -188,8 +186,23 @@ struct crgpu_scene {
 /* ---- node graph checks -------------------------------------------------------------------------------------- */
 static bool node_ok(const crs_scene *f, int idx) { return idx >= 0 && (uint32_t)idx < f->node_count; }
 
-/* nesting depth of color->value->color recursion below a color/value node (checker A/B are tail calls) */
+/* nesting depth below a color / value / vector node as the device interpreter counts it (NodeEval<D>: every evaluation of a child
+ * of another node class, and every math / vecmath / combine operand, goes one level down; grayscale/alpha -> color and the checker's
+ * A/B tail calls do not) */
 static int value_depth(const crs_scene *f, int idx, int guard);
+static int vector_depth(const crs_scene *f, int idx, int guard) {
+	if (!node_ok(f, idx) || guard > 64) return 1000;
+	const crs_node &n = f->nodes[idx];
+	switch (n.kind) {
+	case CRS_VECTOR_CONSTANT: case CRS_VECTOR_NORMAL: return 0;
+	case CRS_VECTOR_VECMATH: {
+		if (n.options >= CRS_VEC_OP_COUNT) return 1000;
+		const int a = vector_depth(f, n.in[0], guard + 1), b = vector_depth(f, n.in[1], guard + 1);
+		return 1 + (a > b ? a : b);
+	}
+	default: return 1000;
+	}
+}
 static int color_depth(const crs_scene *f, int idx, int guard) {
 	if (!node_ok(f, idx) || guard > 64) return 1000;
 	const crs_node &n = f->nodes[idx];
@@ -201,7 +214,13 @@ static int color_depth(const crs_scene *f, int idx, int guard) {
 		int m = a > b ? a : b;
 		return m > v ? m : v;
 	}
-	case CRS_COLOR_BLACKBODY: return 1 + value_depth(f, n.in[0], guard + 1);
+	case CRS_COLOR_BLACKBODY: case CRS_COLOR_COMBINE_VALUE: return 1 + value_depth(f, n.in[0], guard + 1);
+	case CRS_COLOR_COMBINE_RGB: {
+		int m = value_depth(f, n.in[0], guard + 1);
+		for (int k = 1; k < 3; ++k) { const int d = value_depth(f, n.in[k], guard + 1); if (d > m) m = d; }
+		return 1 + m;
+	}
+	case CRS_COLOR_VECTOCOLOR: return 1 + vector_depth(f, n.in[0], guard + 1);
 	default: return 1000;
 	}
 }
@@ -209,8 +228,16 @@ static int value_depth(const crs_scene *f, int idx, int guard) {
 	if (!node_ok(f, idx) || guard > 64) return 1000;
 	const crs_node &n = f->nodes[idx];
 	switch (n.kind) {
-	case CRS_VALUE_CONSTANT: return 0;
+	case CRS_VALUE_CONSTANT: case CRS_VALUE_RAYLENGTH: return 0;
 	case CRS_VALUE_GRAYSCALE: case CRS_VALUE_ALPHA: return color_depth(f, n.in[0], guard + 1);
+	case CRS_VALUE_MATH: {
+		if (n.options >= CRS_MATH_OP_COUNT) return 1000;
+		const int a = value_depth(f, n.in[0], guard + 1), b = value_depth(f, n.in[1], guard + 1);
+		return 1 + (a > b ? a : b);
+	}
+	case CRS_VALUE_FRESNEL:                              /* the normal input is never evaluated (fresnel.c:43-55) but must be a vector node */
+		if (vector_depth(f, n.in[1], guard + 1) >= 1000) return 1000;
+		return 1 + value_depth(f, n.in[0], guard + 1);
 	default: return 1000;
 	}
 }
@@ -218,15 +245,21 @@ static bool color_reads_uv(const crs_scene *f, int idx);
 static bool value_reads_uv(const crs_scene *f, int idx) {
 	if (!node_ok(f, idx)) return false;
 	const crs_node &n = f->nodes[idx];
-	return (n.kind == CRS_VALUE_GRAYSCALE || n.kind == CRS_VALUE_ALPHA) && color_reads_uv(f, n.in[0]);
+	switch (n.kind) {
+	case CRS_VALUE_GRAYSCALE: case CRS_VALUE_ALPHA: return color_reads_uv(f, n.in[0]);
+	case CRS_VALUE_MATH: return value_reads_uv(f, n.in[0]) || value_reads_uv(f, n.in[1]);
+	case CRS_VALUE_FRESNEL: return value_reads_uv(f, n.in[0]);
+	default: return false;
+	}
 }
 static bool color_reads_uv(const crs_scene *f, int idx) {
 	if (!node_ok(f, idx)) return false;
 	const crs_node &n = f->nodes[idx];
 	switch (n.kind) {
 	case CRS_COLOR_IMAGE: case CRS_COLOR_CHECKER: return true;
-	case CRS_COLOR_BLACKBODY: return value_reads_uv(f, n.in[0]);
-	default: return false;
+	case CRS_COLOR_BLACKBODY: case CRS_COLOR_COMBINE_VALUE: return value_reads_uv(f, n.in[0]);
+	case CRS_COLOR_COMBINE_RGB: return value_reads_uv(f, n.in[0]) || value_reads_uv(f, n.in[1]) || value_reads_uv(f, n.in[2]);
+	default: return false;            /* vector nodes never read uv */
 	}
 }
 /* validates a bsdf tree; *add_depth = nesting of ADD nodes; *uv = some node reads uv */

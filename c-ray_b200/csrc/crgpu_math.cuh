@@ -43,6 +43,8 @@ CRN float cr_powf(float x, float y) {
 /* powf(x, 5.0f) as used by schlick() (vector.h:271): four fp64 products, one rounding */
 CRD float cr_pow5f(float x) { const double a = (double)x, a2 = a * a; return (float)(a2 * a2 * a); }
 CRN float cr_logf(float x) { return (float)log((double)x); }
+CRN float cr_log10f(float x) { return (float)log10((double)x); }     /* math.c:66 */
+CRN float cr_tanf(float x) { return (float)tan((double)x); }         /* math.c:87 */
 CRN float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
 CRN float cr_acosf(float x) { return (float)acos((double)x); }
 CRN float cr_asinf(float x) { return (float)asin((double)x); }

@@ -17,6 +17,9 @@
  *   Instance  128 B: Ainv and A (3x4 rows each), kind, object parameters.
  */
 #pragma once
+/* limits of the device node interpreter (crgpu_shade.cuh), enforced at upload (crgpu_api.cu check_bsdf) */
+#define CRG_NODE_DEPTH 8      /* nesting of color / value / vector evaluations below a bsdf input */
+#define CRG_ADD_STACK 4       /* operand stack of nested ADD bsdfs */
 #include <stdint.h>
 #include "../../include/crscene.h"
 

@@ -20,16 +20,13 @@
 #include "crgpu_scene.cuh"
 #include "crgpu_trace.cuh"
 
-#ifndef CRG_NODE_DEPTH
-#define CRG_NODE_DEPTH 3      /* color->value->color nesting supported by the interpreter */
-#define CRG_ADD_STACK 4
-#endif
 
 struct Rec {                  /* the fields of struct hitRecord (hitrecord.h:14-23) the nodes read */
 	v3 inc_d;                 /* incident.direction */
 	v3 p, n;                  /* hitPoint, surfaceNormal */
 	v2 uv;
 	float IOR;                /* material.IOR */
+	float dist;               /* distance (input/raylength.c:39); FLT_MAX on a miss (pathtrace.c:27) */
 };
 
 struct BsdfSample { v3 out; col4 color; };
@@ -117,7 +114,53 @@ template <int D> struct NodeEval {
 	static __device__ __noinline__ col4 color(const DevScene &sc, int node, const Rec &rec);
 	static __device__ __noinline__ float value(const DevScene &sc, int node, const Rec &rec);
 	static __device__ __noinline__ float alpha(const DevScene &sc, int node, const Rec &rec);
+	static __device__ __noinline__ v3 vector(const DevScene &sc, int node, const Rec &rec);
 };
+
+/* converter/math.c:44-97 (libm calls through the fp64 stand-ins of crgpu_math.cuh) */
+static __device__ __noinline__ float cr_math_op(unsigned op, float a, float b) {
+	switch (op) {
+	case CRS_MATH_ADD: return a + b;
+	case CRS_MATH_SUBTRACT: return a - b;
+	case CRS_MATH_MULTIPLY: return a * b;
+	case CRS_MATH_DIVIDE: return cr_div(a, b);
+	case CRS_MATH_POWER: return cr_powf(a, b);
+	case CRS_MATH_LOG: return cr_log10f(a);
+	case CRS_MATH_SQRT: return cr_sqrtf(a);
+	case CRS_MATH_ABS: return fabsf(a);
+	case CRS_MATH_MIN: return CR_MIN(a, b);
+	case CRS_MATH_MAX: return CR_MAX(a, b);
+	case CRS_MATH_SINE: return cr_sinf(a);
+	case CRS_MATH_COSINE: return cr_cosf(a);
+	case CRS_MATH_TANGENT: return cr_tanf(a);
+	case CRS_MATH_TO_RADIANS: return cr_div(a * CR_PI, 180.0f);                          /* transforms.c:18-20 */
+	case CRS_MATH_TO_DEGREES: return a * cr_div(180.0f, CR_PI);                          /* transforms.c:22-24 */
+	default: return 0.0f;
+	}
+}
+/* converter/vecmath.c:43-83: the .v member of struct vectorValue; VecDot / VecLength fill .f only and leave .v zero */
+static __device__ __noinline__ v3 cr_vec_op(unsigned op, v3 a, v3 b) {
+	switch (op) {
+	case CRS_VEC_ADD: return v3add(a, b);
+	case CRS_VEC_SUBTRACT: return v3sub(a, b);
+	case CRS_VEC_MULTIPLY: return v3mul(a, b);
+	case CRS_VEC_AVERAGE: return v3scale(v3add(a, b), 0.5f);
+	case CRS_VEC_CROSS: return v3cross(a, b);
+	case CRS_VEC_NORMALIZE: return v3norm(a);
+	case CRS_VEC_REFLECT: return v3reflect(a, b);
+	case CRS_VEC_ABS: return v3make(fabsf(a.x), fabsf(a.y), fabsf(a.z));
+	default: return v3make(0.0f, 0.0f, 0.0f);
+	}
+}
+CRD float cr_schlick(float cosine, float IOR);
+/* input/fresnel.c:43-55 (IOR already evaluated; the reference evaluates it twice, the value is the same) */
+CRD float cr_fresnel_value(const Rec &rec, float IOR) {
+	float cosine;
+	const float dn = v3dot(rec.inc_d, rec.n);
+	if (dn > 0.0f) cosine = cr_div(IOR * v3dot(rec.inc_d, rec.n), v3len(rec.inc_d));
+	else cosine = -cr_div(v3dot(rec.inc_d, rec.n), v3len(rec.inc_d));
+	return cr_schlick(cosine, IOR);
+}
 
 static __device__ __noinline__ col4 cr_image_color(const DevScene &sc, const crs_node &n, const Rec &rec) {            /* image.c:31-48 */
 	if (n.tex < 0) return c4make(1.0f, 0.0f, 0.5f, 1.0f);
@@ -167,8 +210,36 @@ __device__ __noinline__ col4 NodeEval<D>::color(const DevScene &sc, int node, co
 		}
 		case CRS_COLOR_BLACKBODY:                                                           /* blackbody.c:38-42 */
 			return cr_color_for_kelvin(NodeEval<D - 1>::value(sc, n.in[0], rec));
+		case CRS_COLOR_VECTOCOLOR: {                                                        /* vectocolor.c:38-43 */
+			const v3 v = NodeEval<D - 1>::vector(sc, n.in[0], rec);
+			return c4make(v.x, v.y, v.z, 0.0f);
+		}
+		case CRS_COLOR_COMBINE_VALUE: {                                                     /* combine.c:38-43 */
+			const float v = NodeEval<D - 1>::value(sc, n.in[0], rec);
+			return c4make(v, v, v, 1.0f);
+		}
+		case CRS_COLOR_COMBINE_RGB: {                                                       /* combinergb.c:44-53 */
+			const float r = NodeEval<D - 1>::value(sc, n.in[0], rec);
+			const float g = NodeEval<D - 1>::value(sc, n.in[1], rec);
+			const float b = NodeEval<D - 1>::value(sc, n.in[2], rec);
+			return c4make(r, g, b, 1.0f);
+		}
 		default: return c4make(0.0f, 0.0f, 0.0f, 1.0f);
 		}
+	}
+}
+template <int D>
+__device__ __noinline__ v3 NodeEval<D>::vector(const DevScene &sc, int node, const Rec &rec) {
+	const crs_node &n = sc.nodes[node];
+	switch (n.kind) {
+	case CRS_VECTOR_CONSTANT: return v3make(n.f[0], n.f[1], n.f[2]);                        /* vectornode.c:38-42 */
+	case CRS_VECTOR_NORMAL: return rec.n;                                                   /* normal.c:36-40 */
+	case CRS_VECTOR_VECMATH: {
+		const v3 a = NodeEval<D - 1>::vector(sc, n.in[0], rec);
+		const v3 b = NodeEval<D - 1>::vector(sc, n.in[1], rec);
+		return cr_vec_op(n.options, a, b);
+	}
+	default: return v3make(0.0f, 0.0f, 0.0f);
 	}
 }
 template <int D>
@@ -178,6 +249,13 @@ __device__ __noinline__ float NodeEval<D>::value(const DevScene &sc, int node, c
 	case CRS_VALUE_CONSTANT: return n.f[0];
 	case CRS_VALUE_GRAYSCALE: return cr_grayscale(NodeEval<D>::color(sc, n.in[0], rec));    /* grayscale.c:40-43 */
 	case CRS_VALUE_ALPHA: return NodeEval<D>::alpha(sc, n.in[0], rec);                      /* alpha.c:38-41 */
+	case CRS_VALUE_MATH: {
+		const float a = NodeEval<D - 1>::value(sc, n.in[0], rec);
+		const float b = NodeEval<D - 1>::value(sc, n.in[1], rec);
+		return cr_math_op(n.options, a, b);
+	}
+	case CRS_VALUE_FRESNEL: return cr_fresnel_value(rec, NodeEval<D - 1>::value(sc, n.in[0], rec));
+	case CRS_VALUE_RAYLENGTH: return rec.dist;                                              /* raylength.c:36-40 */
 	default: return 0.0f;
 	}
 }
@@ -208,7 +286,16 @@ template <> struct NodeEval<0> {   /* leaves only */
 		case CRS_VALUE_CONSTANT: return n.f[0];
 		case CRS_VALUE_GRAYSCALE: return cr_grayscale(color(sc, n.in[0], rec));
 		case CRS_VALUE_ALPHA: return alpha(sc, n.in[0], rec);
+		case CRS_VALUE_RAYLENGTH: return rec.dist;
 		default: return 0.0f;
+		}
+	}
+	static __device__ __noinline__ v3 vector(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_VECTOR_CONSTANT: return v3make(n.f[0], n.f[1], n.f[2]);
+		case CRS_VECTOR_NORMAL: return rec.n;
+		default: return v3make(0.0f, 0.0f, 0.0f);
 		}
 	}
 	static __device__ __noinline__ float alpha(const DevScene &sc, int node, const Rec &rec) {
@@ -379,6 +466,7 @@ static __device__ __noinline__ col4 cr_sample_background(const DevScene &sc, v3 
 	rec.n = v3make(0.0f, 0.0f, 0.0f);
 	rec.uv.x = 0.0f; rec.uv.y = 0.0f;
 	rec.IOR = 0.0f;
+	rec.dist = CR_FLT_MAX;                                                                   /* pathtrace.c:27 */
 	const v3 ud = v3norm(dir);
 	const float phi = cr_div(cr_atan2f(ud.z, ud.x), 4.0f) + Nodes::value(sc, n.in[2], rec);
 	const float theta = cr_acosf(cr_div(-ud.y, 1.0f));
@@ -420,6 +508,7 @@ CRD int cr_reconstruct_hit(const DevScene &sc, v3 o, v3 d, const Hit &hit, Rec &
 	cr_object_ray(Ainv, __uint_as_float(meta.z), o, d, oo, od);
 	const v3 p_obj = v3add(oo, v3scale(od, hit.t));                                         /* alongRay(copy, t) */
 	rec.inc_d = d;
+	rec.dist = hit.t;
 	int material;
 	if (meta.x == CRS_INST_MESH) {
 		const uint32_t poly = __ldg(sc.slot_poly + hit.prim);

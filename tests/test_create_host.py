@@ -11,7 +11,7 @@ import subprocess
 
 import pytest
 
-from conftest import ROOT, GOLDEN, GOLDEN_SCENES
+from conftest import ROOT, GOLDEN, GOLDEN_SCENES, GOLDEN_FLAT
 
 PKG = os.path.join(ROOT, "c-ray_b200")
 
@@ -41,7 +41,7 @@ def uploads(exe, scene, threads):
     return int(m.group(1)), m.group(2)
 
 
-@pytest.mark.parametrize("name", GOLDEN_SCENES)
+@pytest.mark.parametrize("name", GOLDEN_FLAT)
 def test_upload_bytes_do_not_depend_on_host_threads(harness, name):
     scene = os.path.join(GOLDEN, name + ".crscene")
     a, b, c = uploads(harness, scene, 1), uploads(harness, scene, 3), uploads(harness, scene, 8)

@@ -14,7 +14,7 @@ import pytest
 
 import crgpu
 import oracle_lib as O
-from conftest import GOLDEN, GOLDEN_SCENES, BUILT
+from conftest import GOLDEN, GOLDEN_SCENES, GOLDEN_FLAT, BUILT
 
 pytestmark = pytest.mark.gpu
 RMSE_BOUND = 1e-4   # BASELINE.json north_star
@@ -28,7 +28,7 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
-@pytest.mark.parametrize("name", GOLDEN_SCENES)
+@pytest.mark.parametrize("name", GOLDEN_FLAT)
 def test_known_answer_records(name):
     h = np.fromfile(os.path.join(GOLDEN, name + ".hits.bin"), dtype=O.HIT_KAT_DTYPE)
     g = crgpu.GpuScene(os.path.join(GOLDEN, name + ".crscene"))
@@ -53,7 +53,7 @@ def test_known_answer_records(name):
     g.close()
 
 
-@pytest.mark.parametrize("name", GOLDEN_SCENES)
+@pytest.mark.parametrize("name", GOLDEN_FLAT)
 def test_framebuffer_vs_reference_golden(name):
     g = crgpu.GpuScene(os.path.join(GOLDEN, name + ".crscene"))
     ref = np.fromfile(os.path.join(GOLDEN, name + ".f32"), dtype=np.float32).reshape(g.H, g.W, 3)

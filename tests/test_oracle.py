@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from conftest import GOLDEN, GOLDEN_SCENES, BUILT
+from conftest import GOLDEN, GOLDEN_SCENES, GOLDEN_FLAT, BUILT
 
 
 def test_sampler_kat_bit_exact():
@@ -35,7 +35,7 @@ def test_draw_range_inclusive_one():
     assert v.min() >= 0.0 and v.max() <= 1.0
 
 
-@pytest.mark.parametrize("name", GOLDEN_SCENES)
+@pytest.mark.parametrize("name", GOLDEN_FLAT)
 def test_framebuffer_bit_exact(name):
     sc = O.OracleScene(os.path.join(GOLDEN, name + ".crscene"))
     ref = np.fromfile(os.path.join(GOLDEN, name + ".f32"), dtype=np.float32).reshape(sc.H, sc.W, 3)
@@ -44,7 +44,7 @@ def test_framebuffer_bit_exact(name):
     sc.close()
 
 
-@pytest.mark.parametrize("name", GOLDEN_SCENES)
+@pytest.mark.parametrize("name", GOLDEN_FLAT)
 def test_hit_records_bit_exact(name):
     sc = O.OracleScene(os.path.join(GOLDEN, name + ".crscene"))
     h = np.fromfile(os.path.join(GOLDEN, name + ".hits.bin"), dtype=O.HIT_KAT_DTYPE)
@@ -55,7 +55,7 @@ def test_hit_records_bit_exact(name):
     sc.close()
 
 
-@pytest.mark.parametrize("name", GOLDEN_SCENES)
+@pytest.mark.parametrize("name", GOLDEN_FLAT)
 def test_tiles_and_pass_ranges_compose(name):
     """Tile size, thread count and splitting the passes never change a pixel (renderer.c:271-320)."""
     sc = O.OracleScene(os.path.join(GOLDEN, name + ".crscene"))
