@@ -392,12 +392,16 @@ def main():
     trace_s = prof["trace_ms"] / 1e3
     shade_s = prof["shade_ms"] / 1e3
     achieved = (prof["rays"] * b_ray / trace_s / 1e9) if trace_s > 0 else None
-    traffic, traffic_note = None, None
+    traffic, traffic_note, issue = None, None, None
     try:   # DRAM bytes of one K2 launch from the committed ncu --set full capture (not live: ncu replays kernels ~40x)
         import glob
         mfile = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_metrics.json")))[-1]
         m = json.load(open(mfile))["kernels"]["k_trace"][0]
         traffic = int((m["dram_read"] + m["dram_write"]) * 1e9)
+        issue = {"active_threads_per_warp_inst": round(m["active_threads_per_warp_inst"], 2), "issue_active_pct": round(m["issue_active_pct"], 1),
+                 "warps_active_pct": round(m["warps_active_pct"], 1),
+                 "dram_gbs": round((m["dram_read"] + m["dram_write"]) / (m["duration"] / 1e3), 1),
+                 "note": "what actually limits k_trace (same ncu capture): instruction issue at ~half the SIMT lanes, not DRAM"}
         traffic_note = (f"{os.path.basename(mfile)}: k_trace bounce-1 launch of a 66M-path batch on input/hdr.json ({m['duration']:.2f} ms): "
                         f"{traffic / 1e9:.2f} GB of DRAM traffic, far BELOW the algorithmic figure because nodes and triangles are served by L1/L2")
     except Exception:   # noqa: BLE001
@@ -405,7 +409,7 @@ def main():
     shade_bytes = 116.0    # K3 per ray: 68 B in (ray 48 + hit 20) + 48 B out when the path survives
     roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 2) if achieved else None, "peak": peak,
                 "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
+                "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_note": traffic_note, "sm_issue": issue,
                 "bytes_per_ray": round(b_ray, 1), "per_ray": {"P": round(P, 3), "T": round(T, 3), "I": round(I, 3), "S": round(S, 3)},
                 "trace_share_of_step": round(prof["trace_ms"] / prof["total_ms"], 4) if prof["total_ms"] else None,
                 "shade_share_of_step": round(prof["shade_ms"] / prof["total_ms"], 4) if prof["total_ms"] else None,

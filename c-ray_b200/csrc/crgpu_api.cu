@@ -148,6 +148,7 @@ struct crgpu_prepared {
 	float world_lo[3], world_inv[3];
 	uint32_t stage_pairs;
 	uint32_t texture_count;
+	bool xnodes;               /* some node is of a kind only the complete interpreter (NodeX) evaluates */
 	uint8_t *slab;
 	bool pinned;
 	size_t slab_bytes;
@@ -157,6 +158,7 @@ struct crgpu_prepared {
 struct crgpu_scene {
 	int device;
 	int sm_count;
+	bool xnodes;               /* crgpu_prepared::xnodes: selects the K3 / tail kernels with the complete node interpreter */
 	cudaStream_t stream;       /* the stream work is enqueued on (own_stream unless crgpu_set_stream) */
 	cudaStream_t own_stream;
 	unsigned long long fetched[8];   /* device counters at the previous stats fetch */
@@ -186,23 +188,51 @@ struct crgpu_scene {
 /* ---- node graph checks -------------------------------------------------------------------------------------- */
 static bool node_ok(const crs_scene *f, int idx) { return idx >= 0 && (uint32_t)idx < f->node_count; }
 
-/* nesting depth below a color / value / vector node as the device interpreter counts it (NodeEval<D>: every evaluation of a child
- * of another node class, and every math / vecmath / combine operand, goes one level down; grayscale/alpha -> color and the checker's
- * A/B tail calls do not) */
-static int value_depth(const crs_scene *f, int idx, int guard);
-static int vector_depth(const crs_scene *f, int idx, int guard) {
+/* Nesting as the device counts it (crgpu_shade.cuh).  The hot interpreter NodeEval<CRG_NODE_DEPTH> knows the node kinds of JSON
+ * scenes: color->value->color recursion costs a level at checker/blackbody -> value (grayscale/alpha -> color and the checker's
+ * A/B tail calls are free).  At the first node of any other kind the complete interpreter NodeX<CRG_XNODE_DEPTH> takes over, where
+ * EVERY edge costs a level (xnode_depth) whatever the kinds below. */
+static int xnode_depth(const crs_scene *f, int idx, int guard) {
 	if (!node_ok(f, idx) || guard > 64) return 1000;
 	const crs_node &n = f->nodes[idx];
+	int ins = 0;
 	switch (n.kind) {
+	case CRS_COLOR_CONSTANT: case CRS_COLOR_IMAGE: case CRS_COLOR_GRADIENT: case CRS_VALUE_CONSTANT: case CRS_VALUE_RAYLENGTH:
 	case CRS_VECTOR_CONSTANT: case CRS_VECTOR_NORMAL: return 0;
-	case CRS_VECTOR_VECMATH: {
-		if (n.options >= CRS_VEC_OP_COUNT) return 1000;
-		const int a = vector_depth(f, n.in[0], guard + 1), b = vector_depth(f, n.in[1], guard + 1);
-		return 1 + (a > b ? a : b);
+	case CRS_COLOR_CHECKER: case CRS_COLOR_COMBINE_RGB: ins = 3; break;
+	case CRS_VALUE_MATH: if (n.options >= CRS_MATH_OP_COUNT) return 1000; ins = 2; break;
+	case CRS_VECTOR_VECMATH: if (n.options >= CRS_VEC_OP_COUNT) return 1000; ins = 2; break;
+	case CRS_COLOR_BLACKBODY: case CRS_COLOR_COMBINE_VALUE: case CRS_COLOR_VECTOCOLOR: case CRS_VALUE_GRAYSCALE: case CRS_VALUE_ALPHA: ins = 1; break;
+	case CRS_VALUE_FRESNEL: {                            /* in1 (normal) is never evaluated (fresnel.c:43-55) but must be a vector node */
+		if (!node_ok(f, n.in[1])) return 1000;
+		const int k = f->nodes[n.in[1]].kind;
+		if (k != CRS_VECTOR_CONSTANT && k != CRS_VECTOR_NORMAL && k != CRS_VECTOR_VECMATH) return 1000;
+		ins = 1; break;
 	}
 	default: return 1000;
 	}
+	/* operand classes: what each input must be */
+	int m = 0;
+	for (int k = 0; k < ins; ++k) {
+		if (!node_ok(f, n.in[k])) return 1000;
+		const int ck = f->nodes[n.in[k]].kind;
+		const bool is_color = ck >= CRS_COLOR_CONSTANT && ck <= CRS_COLOR_COMBINE_RGB, is_value = ck >= CRS_VALUE_CONSTANT && ck <= CRS_VALUE_RAYLENGTH,
+				   is_vector = ck >= CRS_VECTOR_CONSTANT && ck <= CRS_VECTOR_VECMATH;
+		bool ok;
+		switch (n.kind) {
+		case CRS_COLOR_CHECKER: ok = k < 2 ? is_color : is_value; break;
+		case CRS_VALUE_GRAYSCALE: case CRS_VALUE_ALPHA: ok = is_color; break;
+		case CRS_COLOR_VECTOCOLOR: case CRS_VECTOR_VECMATH: ok = is_vector; break;
+		default: ok = is_value; break;                   /* blackbody, combine, combine rgb, math, fresnel (IOR) */
+		}
+		if (!ok) return 1000;
+		const int d = xnode_depth(f, n.in[k], guard + 1);
+		if (d > m) m = d;
+	}
+	return 1 + m;
 }
+static int xnode_entry(const crs_scene *f, int idx, int guard) { return xnode_depth(f, idx, guard) <= CRG_XNODE_DEPTH ? 0 : 1000; }
+static int value_depth(const crs_scene *f, int idx, int guard);
 static int color_depth(const crs_scene *f, int idx, int guard) {
 	if (!node_ok(f, idx) || guard > 64) return 1000;
 	const crs_node &n = f->nodes[idx];
@@ -214,13 +244,8 @@ static int color_depth(const crs_scene *f, int idx, int guard) {
 		int m = a > b ? a : b;
 		return m > v ? m : v;
 	}
-	case CRS_COLOR_BLACKBODY: case CRS_COLOR_COMBINE_VALUE: return 1 + value_depth(f, n.in[0], guard + 1);
-	case CRS_COLOR_COMBINE_RGB: {
-		int m = value_depth(f, n.in[0], guard + 1);
-		for (int k = 1; k < 3; ++k) { const int d = value_depth(f, n.in[k], guard + 1); if (d > m) m = d; }
-		return 1 + m;
-	}
-	case CRS_COLOR_VECTOCOLOR: return 1 + vector_depth(f, n.in[0], guard + 1);
+	case CRS_COLOR_BLACKBODY: return 1 + value_depth(f, n.in[0], guard + 1);
+	case CRS_COLOR_VECTOCOLOR: case CRS_COLOR_COMBINE_VALUE: case CRS_COLOR_COMBINE_RGB: return xnode_entry(f, idx, guard);
 	default: return 1000;
 	}
 }
@@ -228,16 +253,9 @@ static int value_depth(const crs_scene *f, int idx, int guard) {
 	if (!node_ok(f, idx) || guard > 64) return 1000;
 	const crs_node &n = f->nodes[idx];
 	switch (n.kind) {
-	case CRS_VALUE_CONSTANT: case CRS_VALUE_RAYLENGTH: return 0;
+	case CRS_VALUE_CONSTANT: return 0;
 	case CRS_VALUE_GRAYSCALE: case CRS_VALUE_ALPHA: return color_depth(f, n.in[0], guard + 1);
-	case CRS_VALUE_MATH: {
-		if (n.options >= CRS_MATH_OP_COUNT) return 1000;
-		const int a = value_depth(f, n.in[0], guard + 1), b = value_depth(f, n.in[1], guard + 1);
-		return 1 + (a > b ? a : b);
-	}
-	case CRS_VALUE_FRESNEL:                              /* the normal input is never evaluated (fresnel.c:43-55) but must be a vector node */
-		if (vector_depth(f, n.in[1], guard + 1) >= 1000) return 1000;
-		return 1 + value_depth(f, n.in[0], guard + 1);
+	case CRS_VALUE_MATH: case CRS_VALUE_FRESNEL: case CRS_VALUE_RAYLENGTH: return xnode_entry(f, idx, guard);
 	default: return 1000;
 	}
 }
@@ -475,6 +493,12 @@ extern "C" int crgpu_prepare(const struct crs_scene *f, crgpu_prepared **out) {
 	crgpu_prepared *p = new crgpu_prepared();
 	p->slab = nullptr; p->pinned = false; p->slab_bytes = 0;
 	p->prefs = f->prefs; p->camera = f->camera; p->background = f->background; p->instance_count = f->instance_count;
+	p->xnodes = false;
+	for (uint32_t i = 0; i < f->node_count; ++i) {
+		const int k = f->nodes[i].kind;
+		if (k == CRS_COLOR_VECTOCOLOR || k == CRS_COLOR_COMBINE_VALUE || k == CRS_COLOR_COMBINE_RGB || k == CRS_VALUE_MATH || k == CRS_VALUE_FRESNEL ||
+			k == CRS_VALUE_RAYLENGTH || k == CRS_VECTOR_CONSTANT || k == CRS_VECTOR_NORMAL || k == CRS_VECTOR_VECMATH) p->xnodes = true;
+	}
 	p->texture_count = f->texture_count;
 #define PFAIL(x) do { int rc_ = (x); if (rc_) return pfail(p, rc_); } while (0)
 
@@ -755,7 +779,7 @@ extern "C" int crgpu_scene_create_prepared(const crgpu_prepared *p, int device, 
 	memset(&s->wb2, 0, sizeof s->wb2);
 	s->wave_sets = 0; s->stream2 = nullptr; s->evAcc[0] = s->evAcc[1] = nullptr; s->evFork = nullptr;
 	s->pixels = nullptr; s->pixel_cap = 0;
-	s->device = device; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->own_stream = nullptr; s->cap_paths = 0;
+	s->device = device; s->xnodes = p->xnodes; s->dev_copy = nullptr; s->fb = nullptr; s->fb8 = nullptr; s->stream = nullptr; s->own_stream = nullptr; s->cap_paths = 0;
 	s->slab = nullptr; s->slab_bytes = 0; s->small = nullptr; s->small_bytes = 0; s->wave = nullptr; s->wave_bytes = 0; s->fb_floats = 0;
 	memset(s->fetched, 0, sizeof s->fetched);
 	s->pend_paths = s->pend_launches = 0; s->pend_trace_ms = s->pend_shade_ms = s->pend_total_ms = 0.f;
@@ -956,13 +980,13 @@ static int render_pixels(crgpu_scene *s, TileDesc base, uint64_t tile_pixels, in
 		if (maxDepth == 0) CU(cudaMemsetAsync(wb.L, 0, (size_t)tile_pixels * (size_t)td.pass_count * sizeof(float4), st));
 		int cur = 0;
 		for (int depth = 0; depth < maxDepth; ++depth) {
-			if (depth >= CRG_TAIL_FROM && !count) { crg_launch_tail(s->dev_copy, wb, cur, depth, maxDepth, st); ++launches; }
+			if (depth >= CRG_TAIL_FROM && !count) { crg_launch_tail(s->dev_copy, wb, cur, depth, maxDepth, s->xnodes, st); ++launches; }
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
 			crg_launch_trace(s->dev, wb, cur, count, dirmode != 0 && depth > 0, grid, st);
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
 			crg_launch_bucket(wb, cur, grid, st);
 			const bool sort_next = dirmode != 0 && depth + 1 < maxDepth;
-			crg_launch_shade(s->dev_copy, wb, cur, depth, maxDepth, sort_next ? dirmode : 0, grid, st);
+			crg_launch_shade(s->dev_copy, wb, cur, depth, maxDepth, sort_next ? dirmode : 0, s->xnodes, grid, st);
 			if (sort_next) { crg_launch_dirsort(wb, cur ^ 1, grid, st); ++launches; }    /* K4b: the next bounce's rays by direction bin */
 			if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); }
 			launches += 2 + (uint64_t)crg_shade_launches_per_bounce();

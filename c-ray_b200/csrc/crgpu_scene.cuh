@@ -18,7 +18,8 @@
  */
 #pragma once
 /* limits of the device node interpreter (crgpu_shade.cuh), enforced at upload (crgpu_api.cu check_bsdf) */
-#define CRG_NODE_DEPTH 8      /* nesting of color / value / vector evaluations below a bsdf input */
+#define CRG_NODE_DEPTH 3      /* color->value->color nesting of the hot interpreter (NodeEval: the node kinds JSON scenes contain) */
+#define CRG_XNODE_DEPTH 8     /* edges below the first node of a kind only the complete interpreter knows (NodeX: SURVEY 8 f4) */
 #define CRG_ADD_STACK 4       /* operand stack of nested ADD bsdfs */
 #include <stdint.h>
 #include "../../include/crscene.h"

@@ -74,11 +74,11 @@ CRD void cr_finish_path(float4 *__restrict__ Lbuf, unsigned id) {
 }
 
 /* returns true when the path continues with (p_next, d_next) and the updated weight / rng / id */
-template <bool MAYBE_MISS = true>
+template <bool X, bool MAYBE_MISS = true>
 CRD bool cr_shade_one(const DevScene &sc, float4 *__restrict__ Lbuf, v3 o, v3 d, const Hit &hit, float &wr, float &wg, float &wbl,
 					  unsigned &id, uint64_t &rng, int depth, int maxDepth, v3 &p_next, v3 &d_next) {
 	if (MAYBE_MISS && hit.inst < 0) {                                                               /* pathtrace.c:39-42 */
-		const col4 bg = cr_sample_background(sc, d);
+		const col4 bg = cr_sample_background<X>(sc, d);
 		cr_add_radiance(Lbuf, id, wr * bg.r, wg * bg.g, wbl * bg.b);
 		return false;
 	}
@@ -88,7 +88,7 @@ CRD bool cr_shade_one(const DevScene &sc, float4 *__restrict__ Lbuf, v3 o, v3 d,
 	if (mat.flags & 2u)                                                               /* pathtrace.c:44 (x + w*0 == x) */
 		cr_add_radiance(Lbuf, id, wr * mat.emission[0], wg * mat.emission[1], wbl * mat.emission[2]);
 	if (depth + 1 < maxDepth) {                                                       /* else: the loop ends, the sample is unused */
-		const BsdfSample s = cr_sample_bsdf(sc, mat.bsdf, rng, rec);                 /* pathtrace.c:46-48 */
+		const BsdfSample s = cr_sample_bsdf<X>(sc, mat.bsdf, rng, rec);              /* pathtrace.c:46-48 */
 		float probability = 1.0f;
 		bool cont = true;
 		if (depth >= 4) {                                                             /* pathtrace.c:50-55 */
@@ -126,7 +126,7 @@ CRD unsigned cr_dir_bin(const DevScene &sc, v3 o, v3 d, int mode) {
  * PART 0: every ray of the queue.  PART 1 / 2: the two halves of a split launch — 1 = the misses (bucket 0 = perm[0 .. counts[4]):
  * background lookup + radiance, the path always ends, nothing to compact), 2 = the hits (perm[counts[4] .. n)).  The miss half
  * needs a third of the registers of the hit half, so it runs at twice the occupancy; on hdr.json 40% of all rays are misses. */
-template <int MINB, int PART>
+template <int MINB, int PART, bool X>
 __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth, int maxDepth, int dirmode, int prefetch) {
 	const DevScene &sc = *scp;
 	const unsigned n = wb.counts[cur];
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 			const float4 b = wb.stB[cur][i];
 			const uint4 c = wb.stC[cur][i];
 			unsigned id = c.y;
-			const col4 bg = cr_sample_background(sc, v3make(a.w, b.x, b.y));                 /* pathtrace.c:39-42 */
+			const col4 bg = cr_sample_background<X>(sc, v3make(a.w, b.x, b.y));                 /* pathtrace.c:39-42 */
 			cr_add_radiance(wb.L, id, b.z * bg.r, b.w * bg.g, __uint_as_float(c.x) * bg.b);
 		}
 		return;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
 			wr = b.z; wg = b.w; wbl = __uint_as_float(c.x);
 			id = c.y;
 			rng = (uint64_t)c.z | ((uint64_t)c.w << 32);
-			alive = cr_shade_one<PART != 2>(sc, wb.L, v3make(a.x, a.y, a.z), v3make(a.w, b.x, b.y), hit, wr, wg, wbl, id, rng, depth, maxDepth, p_next, d_next);
+			alive = cr_shade_one<X, PART != 2>(sc, wb.L, v3make(a.x, a.y, a.z), v3make(a.w, b.x, b.y), hit, wr, wg, wbl, id, rng, depth, maxDepth, p_next, d_next);
 		}
 		/* order-preserving warp compaction, one atomic per warp */
 		const unsigned mask = __ballot_sync(0xffffffffu, alive);
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256, MINB) k_shade(const DevScene *__restrict_
  * zeroes the live count, so the K2/K4/K3 launches that follow find nothing to do. */
 #define CRG_TAIL_MAX 16384u
 
+template <bool X>
 __global__ void __launch_bounds__(128) k_tail(const DevScene *__restrict__ scp, WaveBuffers wb, int cur, int depth0, int maxDepth) {
 	const DevScene &sc = *scp;
 	const unsigned n = wb.counts[cur];
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(128) k_tail(const DevScene *__restrict__ scp, 
 			const Hit hit = cr_closest_hit<false>(sc, o, d, nullptr);
 			++rays;
 			v3 p_next, d_next;
-			if (!cr_shade_one(sc, wb.L, o, d, hit, wr, wg, wbl, id, rng, depth, maxDepth, p_next, d_next)) break;
+			if (!cr_shade_one<X>(sc, wb.L, o, d, hit, wr, wg, wbl, id, rng, depth, maxDepth, p_next, d_next)) break;
 			o = p_next; d = d_next;
 		}
 		atomicAdd(&wb.stats[0], rays);
@@ -307,7 +308,7 @@ __global__ void k_kat(const DevScene *__restrict__ scp, const int32_t *__restric
 	if (hit.inst < 0) {
 		k.polyIndex = -1;
 		s.out = v3make(0.f, 0.f, 0.f);
-		s.color = cr_sample_background(sc, d);
+		s.color = cr_sample_background<true>(sc, d);
 	} else {
 		Rec rec;
 		const int material = cr_reconstruct_hit(sc, o, d, hit, rec, true);
@@ -318,7 +319,7 @@ __global__ void k_kat(const DevScene *__restrict__ scp, const int32_t *__restric
 		k.normal[0] = rec.n.x; k.normal[1] = rec.n.y; k.normal[2] = rec.n.z;
 		const DevMaterial mat = sc.materials[material];
 		k.emission[0] = mat.emission[0]; k.emission[1] = mat.emission[1]; k.emission[2] = mat.emission[2];
-		s = cr_sample_bsdf(sc, mat.bsdf, rng, rec);
+		s = cr_sample_bsdf<true>(sc, mat.bsdf, rng, rec);
 	}
 	k.out[0] = s.out.x; k.out[1] = s.out.y; k.out[2] = s.out.z;
 	k.color[0] = s.color.r; k.color[1] = s.color.g; k.color[2] = s.color.b; k.color[3] = s.color.a;
@@ -329,25 +330,33 @@ __global__ void k_kat(const DevScene *__restrict__ scp, const int32_t *__restric
 void crg_launch_bucket(const WaveBuffers &wb, int cur, int grid, cudaStream_t st) {
 	k_bucket<false><<<grid, 256, 0, st>>>(wb, cur);
 }
-void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, cudaStream_t st) {
-	k_tail<<<128, 128, 0, st>>>(dsc, wb, cur, depth, maxDepth);
+/* X (the last template argument): the scene contains node kinds only the complete interpreter knows (DevScene::has_xnodes, set at
+ * upload) — every other scene runs the kernels in which that interpreter is not even linked */
+void crg_launch_tail(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, bool xnodes, cudaStream_t st) {
+	if (xnodes) k_tail<true><<<128, 128, 0, st>>>(dsc, wb, cur, depth, maxDepth);
+	else k_tail<false><<<128, 128, 0, st>>>(dsc, wb, cur, depth, maxDepth);
 }
 /* CRGPU_SHADE_MINB = 2|3|4 (blocks per SM of the hit/all kernel: 128 / 80 / 64 registers), CRGPU_SHADE_SPLIT = 0|1 (separate
- * miss kernel at 4 blocks per SM) — read once; the defaults are what measured best on hdr.json / venus.json (profiles/) */
-void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int dirmode, int grid, cudaStream_t st) {
+ * miss kernel at 4 blocks per SM), CRGPU_SHADE_PREFETCH = 0|1 — read once; the defaults are what measured best (profiles/) */
+template <bool X>
+static void launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int dirmode, int grid, cudaStream_t st) {
 	static const int minb = [] { const char *e = getenv("CRGPU_SHADE_MINB"); const int v = e ? atoi(e) : 3; return v >= 2 && v <= 4 ? v : 3; }();
 	static const int split = [] { const char *e = getenv("CRGPU_SHADE_SPLIT"); return e ? atoi(e) : 1; }();
 	static const int prefetch = [] { const char *e = getenv("CRGPU_SHADE_PREFETCH"); return e ? atoi(e) : 0; }();
 	if (split) {
-		k_shade<4, 1><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
-		if (minb == 3) k_shade<3, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
-		else if (minb == 4) k_shade<4, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
-		else k_shade<2, 2><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+		k_shade<4, 1, X><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+		if (minb == 3) k_shade<3, 2, X><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+		else if (minb == 4) k_shade<4, 2, X><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+		else k_shade<2, 2, X><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
 		return;
 	}
-	if (minb == 3) k_shade<3, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
-	else if (minb == 4) k_shade<4, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
-	else k_shade<2, 0><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+	if (minb == 3) k_shade<3, 0, X><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+	else if (minb == 4) k_shade<4, 0, X><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+	else k_shade<2, 0, X><<<grid, 256, 0, st>>>(dsc, wb, cur, depth, maxDepth, dirmode, prefetch);
+}
+void crg_launch_shade(const DevScene *dsc, const WaveBuffers &wb, int cur, int depth, int maxDepth, int dirmode, bool xnodes, int grid, cudaStream_t st) {
+	if (xnodes) launch_shade<true>(dsc, wb, cur, depth, maxDepth, dirmode, grid, st);
+	else launch_shade<false>(dsc, wb, cur, depth, maxDepth, dirmode, grid, st);
 }
 void crg_launch_dirsort(const WaveBuffers &wb, int nxt, int grid, cudaStream_t st) {
 	k_bucket<true><<<grid, 256, 0, st>>>(wb, nxt);

@@ -109,14 +109,126 @@ CRD float cr_texture_get_alpha(const DevScene &sc, const DevTexture &t, float x,
 	return top * (1.0f - fy) + bot * fy;
 }
 
-/* ---- color / value nodes ------------------------------------------------------------------------------------------ */
-template <int D> struct NodeEval {
+/* ---- color / value nodes ------------------------------------------------------------------------------------------
+ * Two interpreters.  NodeEval<D> is the hot one: the node kinds a JSON scene can contain (every bundled scene), nesting budget
+ * CRG_NODE_DEPTH.  A node kind it does not know falls through to NodeX<CRG_XNODE_DEPTH> (below): the complete interpreter — the
+ * kinds only the reference's C constructors can build (math, vecmath, fresnel, raylength, normal, vectocolor,
+ * combine) plus the classic kinds again, because once inside a math chain every child may be of either sort — with its own
+ * budget from the point where it takes over.  Keeping the two apart keeps the hot functions as small as they were (measured:
+ * one merged interpreter with an 8-level budget made K3 18% slower on hdr.json, profiles/README.md). */
+static __device__ __noinline__ col4 cr_xnode_color(const DevScene &sc, int node, const Rec &rec);
+static __device__ __noinline__ float cr_xnode_value(const DevScene &sc, int node, const Rec &rec);
+template <int D, bool X> struct NodeEval {
 	static __device__ __noinline__ col4 color(const DevScene &sc, int node, const Rec &rec);
 	static __device__ __noinline__ float value(const DevScene &sc, int node, const Rec &rec);
 	static __device__ __noinline__ float alpha(const DevScene &sc, int node, const Rec &rec);
-	static __device__ __noinline__ v3 vector(const DevScene &sc, int node, const Rec &rec);
 };
 
+static __device__ __noinline__ col4 cr_image_color(const DevScene &sc, const crs_node &n, const Rec &rec) {            /* image.c:31-48 */
+	if (n.tex < 0) return c4make(1.0f, 0.0f, 0.5f, 1.0f);
+	const DevTexture t = sc.textures[n.tex];
+	col4 out;
+	if (n.options & CRS_IMG_NO_BILINEAR) {
+		const float x = rec.uv.x * (float)t.width;
+		const float y = rec.uv.y * (float)t.height;
+		out = cr_texture_get(sc, t, x, y, false);
+	} else {
+		out = cr_texture_get(sc, t, rec.uv.x, rec.uv.y, true);
+	}
+	if (n.options & CRS_IMG_SRGB_TRANSFORM)
+		out = c4make(cr_srgb_to_linear(out.r), cr_srgb_to_linear(out.g), cr_srgb_to_linear(out.b), out.a);
+	return out;
+}
+
+static __device__ __noinline__ float cr_image_alpha(const DevScene &sc, const crs_node &n, const Rec &rec) {
+	if (n.tex < 0) return 1.0f;
+	const DevTexture t = sc.textures[n.tex];
+	if (n.options & CRS_IMG_NO_BILINEAR)
+		return cr_texture_get_alpha(sc, t, rec.uv.x * (float)t.width, rec.uv.y * (float)t.height, false);
+	return cr_texture_get_alpha(sc, t, rec.uv.x, rec.uv.y, true);
+}
+
+CRD col4 cr_gradient(const crs_node &n, const Rec &rec) {                                   /* gradient.c:40-45 */
+	const v3 unit = v3norm(rec.inc_d);
+	const float t = 0.5f * (unit.y + 1.0f);
+	return c4add(c4coef(1.0f - t, c4make(n.f[0], n.f[1], n.f[2], n.f[3])), c4coef(t, c4make(n.f[4], n.f[5], n.f[6], n.f[7])));
+}
+
+template <int D, bool X>
+__device__ __noinline__ col4 NodeEval<D, X>::color(const DevScene &sc, int node, const Rec &rec) {
+	while (true) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_COLOR_CONSTANT: return c4make(n.f[0], n.f[1], n.f[2], n.f[3]);             /* constant.c:39-42 */
+		case CRS_COLOR_IMAGE: return cr_image_color(sc, n, rec);
+		case CRS_COLOR_GRADIENT: return cr_gradient(n, rec);
+		case CRS_COLOR_CHECKER: {                                                           /* checker.c:31-54 */
+			const float coef = NodeEval<D - 1, X>::value(sc, n.in[2], rec);
+			float sines;
+			if (rec.uv.x >= 0) sines = cr_sinf(coef * rec.uv.x) * cr_sinf(coef * rec.uv.y);
+			else sines = cr_sinf(coef * rec.p.x) * cr_sinf(coef * rec.p.y) * cr_sinf(coef * rec.p.z);
+			node = sines < 0.0f ? n.in[0] : n.in[1];
+			continue;                                                                       /* tail call */
+		}
+		case CRS_COLOR_BLACKBODY:                                                           /* blackbody.c:38-42 */
+			return cr_color_for_kelvin(NodeEval<D - 1, X>::value(sc, n.in[0], rec));
+		default: return X ? cr_xnode_color(sc, node, rec) : c4make(0.0f, 0.0f, 0.0f, 1.0f);
+		}
+	}
+}
+template <int D, bool X>
+__device__ __noinline__ float NodeEval<D, X>::value(const DevScene &sc, int node, const Rec &rec) {
+	const crs_node &n = sc.nodes[node];
+	switch (n.kind) {
+	case CRS_VALUE_CONSTANT: return n.f[0];
+	case CRS_VALUE_GRAYSCALE: return cr_grayscale(NodeEval<D, X>::color(sc, n.in[0], rec));    /* grayscale.c:40-43 */
+	case CRS_VALUE_ALPHA: return NodeEval<D, X>::alpha(sc, n.in[0], rec);                      /* alpha.c:38-41 */
+	default: return X ? cr_xnode_value(sc, node, rec) : 0.0f;
+	}
+}
+/* .alpha of a color node without evaluating the rgb lanes when the node kind allows it */
+template <int D, bool X>
+__device__ __noinline__ float NodeEval<D, X>::alpha(const DevScene &sc, int node, const Rec &rec) {
+	const crs_node &n = sc.nodes[node];
+	switch (n.kind) {
+	case CRS_COLOR_CONSTANT: return n.f[3];
+	case CRS_COLOR_IMAGE: return cr_image_alpha(sc, n, rec);
+	case CRS_COLOR_BLACKBODY: return 0.0f;
+	default: return NodeEval<D, X>::color(sc, node, rec).a;
+	}
+}
+template <bool X> struct NodeEval<0, X> {   /* leaves only */
+	static __device__ __noinline__ col4 color(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_COLOR_CONSTANT: return c4make(n.f[0], n.f[1], n.f[2], n.f[3]);
+		case CRS_COLOR_IMAGE: return cr_image_color(sc, n, rec);
+		case CRS_COLOR_GRADIENT: return cr_gradient(n, rec);
+		default: return X ? cr_xnode_color(sc, node, rec) : c4make(0.0f, 0.0f, 0.0f, 1.0f);
+		}
+	}
+	static __device__ __noinline__ float value(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_VALUE_CONSTANT: return n.f[0];
+		case CRS_VALUE_GRAYSCALE: return cr_grayscale(color(sc, n.in[0], rec));
+		case CRS_VALUE_ALPHA: return alpha(sc, n.in[0], rec);
+		default: return X ? cr_xnode_value(sc, node, rec) : 0.0f;
+		}
+	}
+	static __device__ __noinline__ float alpha(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_COLOR_CONSTANT: return n.f[3];
+		case CRS_COLOR_IMAGE: return cr_image_alpha(sc, n, rec);
+		default: return color(sc, node, rec).a;
+		}
+	}
+};
+template <bool X> using NodesT = NodeEval<CRG_NODE_DEPTH, X>;
+
+/* ---- the complete interpreter ---------------------------------------------------------------------------------------
+ * Every edge of the graph costs one level of the budget E (checked at upload: crgpu_api.cu xnode_depth). */
 /* converter/math.c:44-97 (libm calls through the fp64 stand-ins of crgpu_math.cuh) */
 static __device__ __noinline__ float cr_math_op(unsigned op, float a, float b) {
 	switch (op) {
@@ -152,125 +264,80 @@ static __device__ __noinline__ v3 cr_vec_op(unsigned op, v3 a, v3 b) {
 	default: return v3make(0.0f, 0.0f, 0.0f);
 	}
 }
-CRD float cr_schlick(float cosine, float IOR);
-/* input/fresnel.c:43-55 (IOR already evaluated; the reference evaluates it twice, the value is the same) */
-CRD float cr_fresnel_value(const Rec &rec, float IOR) {
+/* input/fresnel.c:43-55 (the reference evaluates IOR twice; the value is the same) */
+static __device__ __noinline__ float cr_fresnel_value(const Rec &rec, float IOR) {
 	float cosine;
 	const float dn = v3dot(rec.inc_d, rec.n);
 	if (dn > 0.0f) cosine = cr_div(IOR * v3dot(rec.inc_d, rec.n), v3len(rec.inc_d));
 	else cosine = -cr_div(v3dot(rec.inc_d, rec.n), v3len(rec.inc_d));
-	return cr_schlick(cosine, IOR);
+	float r0 = cr_div(1.0f - IOR, 1.0f + IOR);                                           /* schlick, vector.h:268-272 */
+	r0 = r0 * r0;
+	return r0 + (1.0f - r0) * cr_pow5f(1.0f - cosine);
 }
 
-static __device__ __noinline__ col4 cr_image_color(const DevScene &sc, const crs_node &n, const Rec &rec) {            /* image.c:31-48 */
-	if (n.tex < 0) return c4make(1.0f, 0.0f, 0.5f, 1.0f);
-	const DevTexture t = sc.textures[n.tex];
-	col4 out;
-	if (n.options & CRS_IMG_NO_BILINEAR) {
-		const float x = rec.uv.x * (float)t.width;
-		const float y = rec.uv.y * (float)t.height;
-		out = cr_texture_get(sc, t, x, y, false);
-	} else {
-		out = cr_texture_get(sc, t, rec.uv.x, rec.uv.y, true);
-	}
-	if (n.options & CRS_IMG_SRGB_TRANSFORM)
-		out = c4make(cr_srgb_to_linear(out.r), cr_srgb_to_linear(out.g), cr_srgb_to_linear(out.b), out.a);
-	return out;
-}
-
-static __device__ __noinline__ float cr_image_alpha(const DevScene &sc, const crs_node &n, const Rec &rec) {
-	if (n.tex < 0) return 1.0f;
-	const DevTexture t = sc.textures[n.tex];
-	if (n.options & CRS_IMG_NO_BILINEAR)
-		return cr_texture_get_alpha(sc, t, rec.uv.x * (float)t.width, rec.uv.y * (float)t.height, false);
-	return cr_texture_get_alpha(sc, t, rec.uv.x, rec.uv.y, true);
-}
-
-CRD col4 cr_gradient(const crs_node &n, const Rec &rec) {                                   /* gradient.c:40-45 */
-	const v3 unit = v3norm(rec.inc_d);
-	const float t = 0.5f * (unit.y + 1.0f);
-	return c4add(c4coef(1.0f - t, c4make(n.f[0], n.f[1], n.f[2], n.f[3])), c4coef(t, c4make(n.f[4], n.f[5], n.f[6], n.f[7])));
-}
-
-template <int D>
-__device__ __noinline__ col4 NodeEval<D>::color(const DevScene &sc, int node, const Rec &rec) {
-	while (true) {
+template <int E> struct NodeX {
+	static __device__ __noinline__ col4 color(const DevScene &sc, int node, const Rec &rec) {
 		const crs_node &n = sc.nodes[node];
 		switch (n.kind) {
-		case CRS_COLOR_CONSTANT: return c4make(n.f[0], n.f[1], n.f[2], n.f[3]);             /* constant.c:39-42 */
+		case CRS_COLOR_CONSTANT: return c4make(n.f[0], n.f[1], n.f[2], n.f[3]);
 		case CRS_COLOR_IMAGE: return cr_image_color(sc, n, rec);
 		case CRS_COLOR_GRADIENT: return cr_gradient(n, rec);
 		case CRS_COLOR_CHECKER: {                                                           /* checker.c:31-54 */
-			const float coef = NodeEval<D - 1>::value(sc, n.in[2], rec);
+			const float coef = NodeX<E - 1>::value(sc, n.in[2], rec);
 			float sines;
 			if (rec.uv.x >= 0) sines = cr_sinf(coef * rec.uv.x) * cr_sinf(coef * rec.uv.y);
 			else sines = cr_sinf(coef * rec.p.x) * cr_sinf(coef * rec.p.y) * cr_sinf(coef * rec.p.z);
-			node = sines < 0.0f ? n.in[0] : n.in[1];
-			continue;                                                                       /* tail call */
+			return NodeX<E - 1>::color(sc, sines < 0.0f ? n.in[0] : n.in[1], rec);
 		}
-		case CRS_COLOR_BLACKBODY:                                                           /* blackbody.c:38-42 */
-			return cr_color_for_kelvin(NodeEval<D - 1>::value(sc, n.in[0], rec));
+		case CRS_COLOR_BLACKBODY: return cr_color_for_kelvin(NodeX<E - 1>::value(sc, n.in[0], rec));
 		case CRS_COLOR_VECTOCOLOR: {                                                        /* vectocolor.c:38-43 */
-			const v3 v = NodeEval<D - 1>::vector(sc, n.in[0], rec);
+			const v3 v = NodeX<E - 1>::vector(sc, n.in[0], rec);
 			return c4make(v.x, v.y, v.z, 0.0f);
 		}
 		case CRS_COLOR_COMBINE_VALUE: {                                                     /* combine.c:38-43 */
-			const float v = NodeEval<D - 1>::value(sc, n.in[0], rec);
+			const float v = NodeX<E - 1>::value(sc, n.in[0], rec);
 			return c4make(v, v, v, 1.0f);
 		}
 		case CRS_COLOR_COMBINE_RGB: {                                                       /* combinergb.c:44-53 */
-			const float r = NodeEval<D - 1>::value(sc, n.in[0], rec);
-			const float g = NodeEval<D - 1>::value(sc, n.in[1], rec);
-			const float b = NodeEval<D - 1>::value(sc, n.in[2], rec);
+			const float r = NodeX<E - 1>::value(sc, n.in[0], rec);
+			const float g = NodeX<E - 1>::value(sc, n.in[1], rec);
+			const float b = NodeX<E - 1>::value(sc, n.in[2], rec);
 			return c4make(r, g, b, 1.0f);
 		}
 		default: return c4make(0.0f, 0.0f, 0.0f, 1.0f);
 		}
 	}
-}
-template <int D>
-__device__ __noinline__ v3 NodeEval<D>::vector(const DevScene &sc, int node, const Rec &rec) {
-	const crs_node &n = sc.nodes[node];
-	switch (n.kind) {
-	case CRS_VECTOR_CONSTANT: return v3make(n.f[0], n.f[1], n.f[2]);                        /* vectornode.c:38-42 */
-	case CRS_VECTOR_NORMAL: return rec.n;                                                   /* normal.c:36-40 */
-	case CRS_VECTOR_VECMATH: {
-		const v3 a = NodeEval<D - 1>::vector(sc, n.in[0], rec);
-		const v3 b = NodeEval<D - 1>::vector(sc, n.in[1], rec);
-		return cr_vec_op(n.options, a, b);
+	static __device__ __noinline__ float value(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_VALUE_CONSTANT: return n.f[0];
+		case CRS_VALUE_GRAYSCALE: return cr_grayscale(NodeX<E - 1>::color(sc, n.in[0], rec));
+		case CRS_VALUE_ALPHA: return NodeX<E - 1>::color(sc, n.in[0], rec).a;
+		case CRS_VALUE_MATH: {
+			const float a = NodeX<E - 1>::value(sc, n.in[0], rec);
+			const float b = NodeX<E - 1>::value(sc, n.in[1], rec);
+			return cr_math_op(n.options, a, b);
+		}
+		case CRS_VALUE_FRESNEL: return cr_fresnel_value(rec, NodeX<E - 1>::value(sc, n.in[0], rec));
+		case CRS_VALUE_RAYLENGTH: return rec.dist;                                          /* raylength.c:36-40 */
+		default: return 0.0f;
+		}
 	}
-	default: return v3make(0.0f, 0.0f, 0.0f);
+	static __device__ __noinline__ v3 vector(const DevScene &sc, int node, const Rec &rec) {
+		const crs_node &n = sc.nodes[node];
+		switch (n.kind) {
+		case CRS_VECTOR_CONSTANT: return v3make(n.f[0], n.f[1], n.f[2]);                    /* vectornode.c:38-42 */
+		case CRS_VECTOR_NORMAL: return rec.n;                                               /* normal.c:36-40 */
+		case CRS_VECTOR_VECMATH: {
+			const v3 a = NodeX<E - 1>::vector(sc, n.in[0], rec);
+			const v3 b = NodeX<E - 1>::vector(sc, n.in[1], rec);
+			return cr_vec_op(n.options, a, b);
+		}
+		default: return v3make(0.0f, 0.0f, 0.0f);
+		}
 	}
-}
-template <int D>
-__device__ __noinline__ float NodeEval<D>::value(const DevScene &sc, int node, const Rec &rec) {
-	const crs_node &n = sc.nodes[node];
-	switch (n.kind) {
-	case CRS_VALUE_CONSTANT: return n.f[0];
-	case CRS_VALUE_GRAYSCALE: return cr_grayscale(NodeEval<D>::color(sc, n.in[0], rec));    /* grayscale.c:40-43 */
-	case CRS_VALUE_ALPHA: return NodeEval<D>::alpha(sc, n.in[0], rec);                      /* alpha.c:38-41 */
-	case CRS_VALUE_MATH: {
-		const float a = NodeEval<D - 1>::value(sc, n.in[0], rec);
-		const float b = NodeEval<D - 1>::value(sc, n.in[1], rec);
-		return cr_math_op(n.options, a, b);
-	}
-	case CRS_VALUE_FRESNEL: return cr_fresnel_value(rec, NodeEval<D - 1>::value(sc, n.in[0], rec));
-	case CRS_VALUE_RAYLENGTH: return rec.dist;                                              /* raylength.c:36-40 */
-	default: return 0.0f;
-	}
-}
-/* .alpha of a color node without evaluating the rgb lanes when the node kind allows it */
-template <int D>
-__device__ __noinline__ float NodeEval<D>::alpha(const DevScene &sc, int node, const Rec &rec) {
-	const crs_node &n = sc.nodes[node];
-	switch (n.kind) {
-	case CRS_COLOR_CONSTANT: return n.f[3];
-	case CRS_COLOR_IMAGE: return cr_image_alpha(sc, n, rec);
-	case CRS_COLOR_BLACKBODY: return 0.0f;
-	default: return NodeEval<D>::color(sc, node, rec).a;
-	}
-}
-template <> struct NodeEval<0> {   /* leaves only */
+};
+template <> struct NodeX<0> {   /* leaves only */
 	static __device__ __noinline__ col4 color(const DevScene &sc, int node, const Rec &rec) {
 		const crs_node &n = sc.nodes[node];
 		switch (n.kind) {
@@ -282,32 +349,15 @@ template <> struct NodeEval<0> {   /* leaves only */
 	}
 	static __device__ __noinline__ float value(const DevScene &sc, int node, const Rec &rec) {
 		const crs_node &n = sc.nodes[node];
-		switch (n.kind) {
-		case CRS_VALUE_CONSTANT: return n.f[0];
-		case CRS_VALUE_GRAYSCALE: return cr_grayscale(color(sc, n.in[0], rec));
-		case CRS_VALUE_ALPHA: return alpha(sc, n.in[0], rec);
-		case CRS_VALUE_RAYLENGTH: return rec.dist;
-		default: return 0.0f;
-		}
+		return n.kind == CRS_VALUE_CONSTANT ? n.f[0] : (n.kind == CRS_VALUE_RAYLENGTH ? rec.dist : 0.0f);
 	}
 	static __device__ __noinline__ v3 vector(const DevScene &sc, int node, const Rec &rec) {
 		const crs_node &n = sc.nodes[node];
-		switch (n.kind) {
-		case CRS_VECTOR_CONSTANT: return v3make(n.f[0], n.f[1], n.f[2]);
-		case CRS_VECTOR_NORMAL: return rec.n;
-		default: return v3make(0.0f, 0.0f, 0.0f);
-		}
-	}
-	static __device__ __noinline__ float alpha(const DevScene &sc, int node, const Rec &rec) {
-		const crs_node &n = sc.nodes[node];
-		switch (n.kind) {
-		case CRS_COLOR_CONSTANT: return n.f[3];
-		case CRS_COLOR_IMAGE: return cr_image_alpha(sc, n, rec);
-		default: return color(sc, node, rec).a;
-		}
+		return n.kind == CRS_VECTOR_CONSTANT ? v3make(n.f[0], n.f[1], n.f[2]) : (n.kind == CRS_VECTOR_NORMAL ? rec.n : v3make(0.0f, 0.0f, 0.0f));
 	}
 };
-typedef NodeEval<CRG_NODE_DEPTH> Nodes;
+static __device__ __noinline__ col4 cr_xnode_color(const DevScene &sc, int node, const Rec &rec) { return NodeX<CRG_XNODE_DEPTH>::color(sc, node, rec); }
+static __device__ __noinline__ float cr_xnode_value(const DevScene &sc, int node, const Rec &rec) { return NodeX<CRG_XNODE_DEPTH>::value(sc, node, rec); }
 
 /* ---- vector.h:252-272 --------------------------------------------------------------------------------------------------- */
 CRD bool cr_refract(v3 in, v3 normal, float niOverNt, v3 &refracted) {
@@ -348,30 +398,31 @@ CRD float cr_fresnel_probability(const Rec &rec, float IOR, v3 &refracted) {
 }
 
 /* one non-composite bsdf node; returns false when `node` is MIX/PLASTIC(diffuse branch)/ADD and sets next */
+template <bool X>
 CRD BsdfSample cr_sample_leaf(const DevScene &sc, const crs_node &n, uint64_t &rng, const Rec &rec) {
 	BsdfSample s;
 	switch (n.kind) {
 	case CRS_BSDF_DIFFUSE:                                                                  /* diffuse.c:40-47 */
 		s.out = v3norm(v3add(rec.n, cr_random_on_unit_sphere(rng)));
-		s.color = Nodes::color(sc, n.in[0], rec);
+		s.color = NodesT<X>::color(sc, n.in[0], rec);
 		return s;
 	case CRS_BSDF_ISOTROPIC:                                                                /* isotropic.c:40-47 */
 		s.out = v3norm(cr_random_on_unit_sphere(rng));
-		s.color = Nodes::color(sc, n.in[0], rec);
+		s.color = NodesT<X>::color(sc, n.in[0], rec);
 		return s;
 	case CRS_BSDF_EMISSIVE: {                                                               /* emission.c:42-49 */
 		s.out = v3norm(v3add(rec.n, cr_random_on_unit_sphere(rng)));
-		const float strength = Nodes::value(sc, n.in[1], rec);
-		s.color = c4coef(strength, Nodes::color(sc, n.in[0], rec));
+		const float strength = NodesT<X>::value(sc, n.in[1], rec);
+		s.color = c4coef(strength, NodesT<X>::color(sc, n.in[0], rec));
 		return s;
 	}
 	case CRS_BSDF_METAL: {                                                                  /* metal.c:40-55 */
 		const v3 nd = v3norm(rec.inc_d);
 		v3 reflected = v3reflect(nd, rec.n);
-		const float rough = Nodes::value(sc, n.in[1], rec);
+		const float rough = NodesT<X>::value(sc, n.in[1], rec);
 		if (rough > 0.0f) reflected = v3add(reflected, v3scale(cr_random_on_unit_sphere(rng), rough));
 		s.out = reflected;
-		s.color = Nodes::color(sc, n.in[0], rec);
+		s.color = NodesT<X>::color(sc, n.in[0], rec);
 		return s;
 	}
 	case CRS_BSDF_GLASS: {                                                                  /* glass.c:41-87 */
@@ -379,21 +430,21 @@ CRD BsdfSample cr_sample_leaf(const DevScene &sc, const crs_node &n, uint64_t &r
 		 * "total internal reflection always reflects" (DESIGN.md deviation #3, same as oracle/cray_oracle.c) */
 		v3 reflected = v3reflect(rec.inc_d, rec.n);
 		v3 refracted = reflected;
-		const float IOR = Nodes::value(sc, n.in[2], rec);
+		const float IOR = NodesT<X>::value(sc, n.in[2], rec);
 		const float prob = cr_fresnel_probability(rec, IOR, refracted);
-		const float rough = Nodes::value(sc, n.in[1], rec);
+		const float rough = NodesT<X>::value(sc, n.in[1], rec);
 		if (rough > 0.0f) {
 			const v3 fuzz = v3scale(cr_random_on_unit_sphere(rng), rough);
 			reflected = v3add(reflected, fuzz);
 			refracted = v3add(refracted, fuzz);
 		}
 		s.out = cr_draw(rng) < prob ? reflected : refracted;
-		s.color = Nodes::color(sc, n.in[0], rec);
+		s.color = NodesT<X>::color(sc, n.in[0], rec);
 		return s;
 	}
 	case CRS_BSDF_TRANSPARENT:                                                              /* transparent.c:40-44 */
 		s.out = rec.inc_d;
-		s.color = Nodes::color(sc, n.in[0], rec);
+		s.color = NodesT<X>::color(sc, n.in[0], rec);
 		return s;
 	default:
 		s.out = v3make(0.0f, 0.0f, 0.0f);
@@ -406,6 +457,7 @@ CRD BsdfSample cr_sample_leaf(const DevScene &sc, const crs_node &n, uint64_t &r
  * PLASTIC→diffuse are tail calls; ADD pushes "combine" + B and continues with A, so A's draws come
  * before B's exactly as add.c:44-45. */
 #define CRG_COMBINE (-2)
+template <bool X>
 CRD BsdfSample cr_sample_bsdf(const DevScene &sc, int root, uint64_t &rng, const Rec &rec) {
 	int todo[CRG_ADD_STACK];
 	BsdfSample vals[CRG_ADD_STACK / 2 + 1];
@@ -417,14 +469,14 @@ CRD BsdfSample cr_sample_bsdf(const DevScene &sc, int root, uint64_t &rng, const
 		while (!have) {
 			const crs_node &n = sc.nodes[node];
 			if (n.kind == CRS_BSDF_MIX) {                                                   /* mix.c:42-50 */
-				const float lerp = Nodes::value(sc, n.in[2], rec);
+				const float lerp = NodesT<X>::value(sc, n.in[2], rec);
 				node = (cr_draw(rng) > lerp) ? n.in[0] : n.in[1];
 			} else if (n.kind == CRS_BSDF_PLASTIC) {                                        /* plastic.c:42-87 */
 				v3 refracted;
 				const float prob = cr_fresnel_probability(rec, rec.IOR, refracted);
 				if (cr_draw(rng) < prob) {                                                  /* sampleShiny :42-56 */
 					v3 reflected = v3reflect(rec.inc_d, rec.n);
-					const float rough = Nodes::color(sc, n.in[1], rec).r;
+					const float rough = NodesT<X>::color(sc, n.in[1], rec).r;
 					if (rough > 0.0f) reflected = v3add(reflected, v3scale(cr_random_on_unit_sphere(rng), rough));
 					s.out = reflected;
 					s.color = c4make(1.0f, 1.0f, 1.0f, 1.0f);
@@ -437,7 +489,7 @@ CRD BsdfSample cr_sample_bsdf(const DevScene &sc, int root, uint64_t &rng, const
 				todo[nt++] = n.in[1];
 				node = n.in[0];
 			} else {
-				s = cr_sample_leaf(sc, n, rng, rec);    /* (an over-deep ADD falls to the black default; rejected at upload) */
+				s = cr_sample_leaf<X>(sc, n, rng, rec);    /* (an over-deep ADD falls to the black default; rejected at upload) */
 				have = true;
 			}
 		}
@@ -458,6 +510,7 @@ CRD BsdfSample cr_sample_bsdf(const DevScene &sc, int root, uint64_t &rng, const
 }
 
 /* scene->background->sample(...) — background.c:39-66 (pathtrace.c:40) */
+template <bool X>
 static __device__ __noinline__ col4 cr_sample_background(const DevScene &sc, v3 dir) {
 	const crs_node &n = sc.nodes[sc.background];
 	Rec rec;
@@ -468,15 +521,15 @@ static __device__ __noinline__ col4 cr_sample_background(const DevScene &sc, v3 
 	rec.IOR = 0.0f;
 	rec.dist = CR_FLT_MAX;                                                                   /* pathtrace.c:27 */
 	const v3 ud = v3norm(dir);
-	const float phi = cr_div(cr_atan2f(ud.z, ud.x), 4.0f) + Nodes::value(sc, n.in[2], rec);
+	const float phi = cr_div(cr_atan2f(ud.z, ud.x), 4.0f) + NodesT<X>::value(sc, n.in[2], rec);
 	const float theta = cr_acosf(cr_div(-ud.y, 1.0f));
 	float u = cr_div(theta, CR_PI);
 	float v = cr_div(phi, CR_PI / 2.0f);
 	u = cr_wrapMinMax(u, 0.0f, 1.0f);
 	v = cr_wrapMinMax(v, 0.0f, 1.0f);
 	rec.uv.x = v; rec.uv.y = u;
-	const float strength = Nodes::value(sc, n.in[1], rec);
-	return c4coef(strength, Nodes::color(sc, n.in[0], rec));
+	const float strength = NodesT<X>::value(sc, n.in[1], rec);
+	return c4coef(strength, NodesT<X>::color(sc, n.in[0], rec));
 }
 
 /* ---- hit reconstruction: everything intersectSphere/intersectMesh do after the closest primitive is known ------------------ */
