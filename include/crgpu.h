@@ -5,7 +5,7 @@
  * src/renderer/renderer.c:40-180) starts worker threads through a `struct crThread` slot whose
  * `threadFunc` is today `renderThread` (renderer.c:258-327) or `networkRenderThread`
  * (src/utils/protocol/server.c:215-263).  A GPU worker thread occupies the same slot
- * (c-ray_b200/host/cr_renderer.c `gpuRenderThread`, reference-side binding in INTEGRATION.md) and calls ONLY the functions
+ * (c-ray_b200/host/cr_renderer.c `gpuRenderThread`; the reference-side binding is c-ray_b200/integration/gpu_thread.c) and calls ONLY the functions
  * below — plain pointers and sizes, no CUDA or torch types.
  *
  *   reference interface replaced                                  entry point here
@@ -18,6 +18,7 @@
  *   colorToSRGB + setPixel(image), renderer.c:297-300              crgpu_framebuffer_to_srgb8
  *   textureGetPixel(renderBuffer), renderer.c:283                  crgpu_framebuffer_read / _write / _clear
  *   tile gather of the cluster mode, server.c:159-174              crgpu_framebuffer_device_ptr (+ NCCL in the host)
+ *   buildBvhGeneric, src/accelerators/bvh.c:245-296                crgpu_bvh_build (optional: the loaders build on the host)
  *
  * All functions return 0 on success or a negative CRGPU_ERR_* code; crgpu_last_error() gives text.
  * The host turns errors into logr(warning|error, ...) like the rest of c-ray (logging.c:50-74).
