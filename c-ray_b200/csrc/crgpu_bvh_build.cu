@@ -426,7 +426,10 @@ extern "C" int crgpu_bvh_build(const float *bboxes, const float *centers, uint32
 		const uint32_t nopen = h[1], go = (nopen + 127u) / 128u;
 		if (nopen > max_open) return crg_fail(CRGPU_ERR_CUDA, "crgpu_bvh_build: %u open nodes for %u primitives", nopen, n);
 		uint32_t *open_list = d_open[cur].as<uint32_t>(), *next_list = d_open[cur ^ 1].as<uint32_t>();
-		k_bins_clear<<<(unsigned)((((size_t)nopen * sizeof(Bins) / 8u) + 255u) / 256u > 65535u ? 65535u : (((size_t)nopen * sizeof(Bins) / 8u) + 255u) / 256u), 256, 0, st>>>(d_bins.as<Bins>(), nopen);
+		{
+			const size_t blocks = ((size_t)nopen * (sizeof(Bins) / 8u) + 255u) / 256u;          /* grid-stride loop inside */
+			k_bins_clear<<<(unsigned)(blocks > 65535u ? 65535u : blocks), 256, 0, st>>>(d_bins.as<Bins>(), nopen);
+		}
 		k_bin<<<gn, 256, 0, st>>>(d_bb.as<float>(), d_ctr.as<float>(), d_prims.as<int32_t>(), d_owner.as<int32_t>(), recs, d_bins.as<Bins>(), n);
 		k_split<<<go, 128, 0, st>>>(d_bb.as<float>(), d_prims.as<int32_t>(), recs, open_list, nopen, d_bins.as<Bins>());
 		k_flag<<<gn, 256, 0, st>>>(d_ctr.as<float>(), d_prims.as<int32_t>(), d_owner.as<int32_t>(), recs, d_flags.as<unsigned long long>(), n);
