@@ -58,7 +58,7 @@ def main():
     print("### bench lines\n")
     print("| file | workload | GPUs | value Mray/s | ms/step | e2e Mray/s | K2 Gray/s | K2 algorithmic frac | B_ray | trace / shade share | CPU reference Mray/s | frame CRC | SM MHz, throttle reasons |")
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
-    for path in sorted(glob.glob(os.path.join(P, rnd + "_bench_*.json"))):
+    for path in sorted(glob.glob(os.path.join(P, rnd + "_bench_*.json")) + glob.glob(os.path.join(P, rnd + "_scale_*.json"))):
         if "reference_arm" in path:
             continue
         print(bench_row("", path))
