@@ -55,11 +55,10 @@ __global__ void __launch_bounds__(256) k_generate(DevScene sc, WaveBuffers wb, T
 #define CRG_NODE_BURST 3
 #define CRG_STAGE_MIN_RAYS 65536u
 #define CRG_DEFER_DEFAULT 0
-#define CRG_REUSE_SETUP_DEFAULT 0   /* measured (profiles/r02_sweeps_call_k.txt) */
 #define CRG_MAX_STEPS 8000000u   /* > 30x the node count of any scene that fits the 2^23-node address space we support */
 
 template <bool COUNT, int MINB, int DEFER>
-__global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb, int cur, int refill, int burst, int sorted, int inst_min, int reuse_setup) {
+__global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb, int cur, int refill, int burst, int sorted, int inst_min) {
 	const unsigned n = wb.counts[cur];
 	const unsigned lane = threadIdx.x & 31u;
 	const float4 *__restrict__ stA = wb.stA[cur];
@@ -98,11 +97,10 @@ __global__ void __launch_bounds__(256, MINB) k_trace(DevScene sc, WaveBuffers wb
 		}
 		snodes = reinterpret_cast<const PairNode *>(s_dyn);
 	}
-	uint32_t stack[CRG_STACK_WORDS];
+	uint32_t stack[2 * CRG_MAX_STACK + 2];
 	Traversal<COUNT> tr;
 	tr.stack = stack;
 	tr.snodes = snodes;
-	tr.reuse = reuse_setup != 0;
 	tr.begin(sc, v3make(0.f, 0.f, 0.f), v3make(0.f, 0.f, 1.f));   /* every lane holds a VALID (idle) state from the start */
 	bool busy = false;
 	bool exhausted = false;          /* warp-uniform: the work counter ran past n */
@@ -229,8 +227,7 @@ static void launch_trace_variant(const DevScene &sc, const WaveBuffers &wb, int 
 	static const int refill = [] { const char *e = getenv("CRGPU_TRACE_REFILL"); const int v = e ? atoi(e) : CRG_REFILL; return v >= 1 && v <= 32 ? v : CRG_REFILL; }();
 	static const int burst = [] { const char *e = getenv("CRGPU_TRACE_BURST"); const int v = e ? atoi(e) : (DEFER ? 4 : CRG_NODE_BURST); return v >= 1 ? v : CRG_NODE_BURST; }();
 	static const int inst_min = [] { const char *e = getenv("CRGPU_TRACE_INSTMIN"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 32 ? v : 8; }();
-	static const int reuse_setup = [] { const char *e = getenv("CRGPU_TRACE_REUSE_SETUP"); return e ? atoi(e) : CRG_REUSE_SETUP_DEFAULT; }();
-	k_trace<COUNT, MINB, DEFER><<<grid, 256, smem, st>>>(sc, wb, cur, refill, burst, sorted ? 1 : 0, inst_min, reuse_setup);
+	k_trace<COUNT, MINB, DEFER><<<grid, 256, smem, st>>>(sc, wb, cur, refill, burst, sorted ? 1 : 0, inst_min);
 }
 
 void crg_launch_trace(const DevScene &sc, const WaveBuffers &wb, int cur, bool count, bool sorted, int grid, cudaStream_t st) {

@@ -206,7 +206,6 @@ CRD void cr_object_ray(const float *Ainv, float ray_offset, v3 o, v3 d, v3 &oo, 
 }
 
 #define CRG_END 0xffffffffu
-#define CRG_STACK_WORDS (2 * CRG_MAX_STACK + 2 + 8)   /* traversal stack + saved world-ray set-up (Traversal::save_world_setup) */
 
 /* getClosestIsect (pathtrace.c:26-30) = traverseTopLevelBvh → intersectTopLevelLeaf → intersectMesh →
  * traverseBottomLevelBvh, flattened into ONE loop so that the 32 lanes of a warp stay convergent:
@@ -236,26 +235,7 @@ struct Traversal {
 	uint32_t leafA, leafB, leafN;          /* DEFER: bottom-level leaf triangles not yet tested — slots [leafA, +nA) then [leafB, +nB), leafN = nA | nB << 16 */
 	int sp, spBase, curInst;
 	bool bottom, instHit;
-	bool reuse;            /* keep the world ray's slab set-up in local memory instead of recomputing it after every mesh (K2 knob) */
-	uint32_t *stack;       /* CRG_STACK_WORDS entries of thread-local memory, owned by the caller (keeps the scalars in registers): the
-	                        * traversal stack in [0, 2*CRG_MAX_STACK+2), the saved world-ray set-up behind it (save_world_setup) */
-
-	/* the slab-test set-up of the WORLD ray is needed again every time a mesh BVH has been left (finish_bottom).  Recomputing it there
-	 * costs three IEEE divisions executed by the ~9 lanes that leave a mesh in the same iteration (ncu, profiles/README.md: 5% of K2's
-	 * warp instructions); seven words of local memory written once per ray and read back per exit are cheaper */
-	CRD void save_world_setup() {
-		uint32_t *w = stack + (2 * CRG_MAX_STACK + 2);
-		w[0] = __float_as_uint(rs.invDir.x); w[1] = __float_as_uint(rs.invDir.y); w[2] = __float_as_uint(rs.invDir.z);
-		w[3] = __float_as_uint(rs.scaledStart.x); w[4] = __float_as_uint(rs.scaledStart.y); w[5] = __float_as_uint(rs.scaledStart.z);
-		w[6] = (rs.ox ? 1u : 0u) | (rs.oy ? 2u : 0u) | (rs.oz ? 4u : 0u) | (rs.deg << 3);
-	}
-	CRD void load_world_setup() {
-		const uint32_t *w = stack + (2 * CRG_MAX_STACK + 2);
-		rs.invDir = v3make(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]));
-		rs.scaledStart = v3make(__uint_as_float(w[3]), __uint_as_float(w[4]), __uint_as_float(w[5]));
-		const uint32_t f = w[6];
-		rs.ox = (f & 1u) != 0u; rs.oy = (f & 2u) != 0u; rs.oz = (f & 4u) != 0u; rs.deg = f >> 3;
-	}
+	uint32_t *stack;       /* 2*CRG_MAX_STACK+2 entries of thread-local memory, owned by the caller (keeps the scalars in registers) */
 
 	CRD bool done() const { return !bottom && (cntA | cntB) == 0u && node == CRG_END && leafN == 0u; }
 
@@ -263,7 +243,6 @@ struct Traversal {
 		best.t = CR_FLT_MAX; best.u = 0.0f; best.v = 0.0f; best.inst = -1; best.prim = 0u;
 		wo = ro; wd = rd; o = ro; d = rd;
 		rs = cr_ray_setup(o, d);
-		if (reuse) save_world_setup();
 		base = sc.pairs + sc.top.pair_offset;
 		stageBase = sc.top.stage_base; stageCount = snodes ? sc.top.stage_count : 0u;
 		tris = sc.tris;
@@ -297,7 +276,7 @@ struct Traversal {
 			if (instHit) best.inst = curInst;
 			bottom = false;
 			o = wo; d = wd;
-			if (reuse) load_world_setup(); else rs = cr_ray_setup(o, d);
+			rs = cr_ray_setup(o, d);
 			base = sc.pairs + sc.top.pair_offset;
 			stageBase = sc.top.stage_base; stageCount = snodes ? sc.top.stage_count : 0u;
 			node = topNext;
@@ -496,11 +475,10 @@ CRD void cr_coop_leaves(Traversal<COUNT> &tr, bool has, const DevScene &sc, Coop
 
 template <bool COUNT>
 CRD Hit cr_closest_hit(const DevScene &sc, v3 wo, v3 wd, TraceCounters *ctr) {
-	uint32_t stack[CRG_STACK_WORDS];
+	uint32_t stack[2 * CRG_MAX_STACK + 2];
 	Traversal<COUNT> tr;
 	tr.stack = stack;
 	tr.snodes = nullptr;
-	tr.reuse = false;
 	tr.begin(sc, wo, wd);
 	while (!tr.done()) tr.step(sc, ctr);
 	return tr.best;
