@@ -221,11 +221,13 @@ void crWriteImage(void) {                                            /* c-ray.c:
 	char *path = NULL;
 	if (asprintf(&path, "%s%s_%04d.%s", g_renderer->prefs.imgFilePath, g_renderer->prefs.imgFileName, g_renderer->prefs.imgCount,
 				 g_renderer->prefs.imgType == png ? "png" : "bmp") < 0) return;
-	if (writeImage(g_image, path, g_renderer->prefs.imgType) != 0) {
+	struct renderInfo info;
+	rendererInfo(g_renderer, &info);
+	if (writeImageInfo(g_image, path, g_renderer->prefs.imgType, &info) != 0) {
 		/* fileio.c:93-109: fall back to the working directory when the output directory is not writable */
 		char *fallback = NULL;
 		if (asprintf(&fallback, "./%s_%04d.%s", g_renderer->prefs.imgFileName, g_renderer->prefs.imgCount,
-					 g_renderer->prefs.imgType == png ? "png" : "bmp") >= 0 && writeImage(g_image, fallback, g_renderer->prefs.imgType) == 0)
+					 g_renderer->prefs.imgType == png ? "png" : "bmp") >= 0 && writeImageInfo(g_image, fallback, g_renderer->prefs.imgType, &info) == 0)
 			printf("[info] Saving result in \"%s\"\n", fallback);
 		else fprintf(stderr, "[warn] Image can't be saved to \"%s\"\n", path);
 		free(fallback);

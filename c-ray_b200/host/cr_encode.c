@@ -2,9 +2,10 @@
  * cr_encode.c — 8-bit sRGB image writers (the step right after the hot path).
  * Same outputs as the reference's encoders: 24-bit bottom-up BMP (src/utils/encoders/formats/bmp.c:19-71)
  * and 8-bit RGB PNG (formats/png.c:24-75; multi-threaded zlib deflate here instead of the vendored lodepng,
- * tEXt metadata omitted).  Pixel values come from crgpu_framebuffer_to_srgb8.
+ * the reference's tEXt labels included).  Pixel values come from crgpu_framebuffer_to_srgb8.
  */
 #include "cr_host.h"
+#include <sys/utsname.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -92,7 +93,24 @@ static void *band_worker(void *arg) {
 	}
 }
 
-int encodePNG(const struct texture8 *img, const char *path) {
+/* png.c:29-56: the reference labels its PNGs with uncompressed tEXt chunks (lodepng text_compression = 0): keyword, NUL, text */
+static void put_text(FILE *f, const char *key, const char *text) {
+	unsigned char buf[1600];
+	const size_t k = strlen(key), t = strlen(text);
+	if (k + 1 + t > sizeof buf) return;
+	memcpy(buf, key, k); buf[k] = 0; memcpy(buf + k + 1, text, t);
+	put_chunk(f, "tEXt", buf, (uint32_t)(k + 1 + t));
+}
+static void smart_time_us(double sec, char *buf, size_t n) {     /* timer.c smartTime */
+	if (sec < 1.0) snprintf(buf, n, "%.0fms", 1e3 * sec);
+	else if (sec < 60.0) snprintf(buf, n, "%.0fs", sec);
+	else if (sec < 3600.0) snprintf(buf, n, "%dm %02ds", (int)(sec / 60.0), (int)sec % 60);
+	else snprintf(buf, n, "%dh %02dm", (int)(sec / 3600.0), ((int)sec % 3600) / 60);
+}
+
+int encodePNG(const struct texture8 *img, const char *path) { return encodePNGInfo(img, path, NULL); }
+
+int encodePNGInfo(const struct texture8 *img, const char *path, const struct renderInfo *info) {
 	const unsigned W = img->width, H = img->height;
 	if (!W || !H) return -1;
 	/* bands of >= 1 MB of scanlines (smaller ones would cost compression ratio: each band starts with an empty window) */
@@ -129,6 +147,20 @@ int encodePNG(const struct texture8 *img, const char *path) {
 		unsigned char ihdr[13] = { (unsigned char)(W >> 24), (unsigned char)(W >> 16), (unsigned char)(W >> 8), (unsigned char)W,
 								   (unsigned char)(H >> 24), (unsigned char)(H >> 16), (unsigned char)(H >> 8), (unsigned char)H, 8, 2, 0, 0, 0 };
 		put_chunk(f, "IHDR", ihdr, 13);
+		if (info) {                                                /* same keywords as png.c:49-56; "Threads" counts GPU workers here */
+			char num[64], sys[1400];
+			put_text(f, "C-ray Version", "c-ray B200 path (libcrgpu.so / libcrhost.so), c-ray's API and file formats (c) 2015-2020 Valtteri Koskivuori");
+			put_text(f, "C-ray Source", "https://github.com/vkoskiv/c-ray");
+			snprintf(num, sizeof num, "%i", info->samples); put_text(f, "C-ray Samples", num);
+			snprintf(num, sizeof num, "%i", info->bounces); put_text(f, "C-ray Bounces", num);
+			smart_time_us(info->renderSeconds, num, sizeof num); put_text(f, "C-ray RenderTime", num);
+			snprintf(num, sizeof num, "%i", info->threadCount); put_text(f, "C-ray Threads", num);
+			struct utsname name;
+			if (uname(&name) == 0) {
+				snprintf(sys, sizeof sys, "%s %s %s %s %s", name.machine, name.nodename, name.release, name.sysname, name.version);
+				put_text(f, "C-ray SysInfo", sys);
+			}
+		}
 		uLong adler = adler32(0L, Z_NULL, 0);
 		for (int i = 0; i < n; ++i) adler = i ? adler32_combine(adler, bands[i].adler, (z_off_t)bands[i].raw) : bands[i].adler;
 		for (int i = 0; i < n; ++i) {
@@ -152,6 +184,16 @@ int encodePNG(const struct texture8 *img, const char *path) {
 }
 
 int writeImage(const struct texture8 *img, const char *path, enum fileType type) {   /* encoder.c:22-39 */
+	return writeImageInfo(img, path, type, NULL);
+}
+int writeImageInfo(const struct texture8 *img, const char *path, enum fileType type, const struct renderInfo *info) {
 	if (!img || !img->data || !path) return -1;
-	return type == bmp ? encodeBMP(img, path) : encodePNG(img, path);
+	return type == bmp ? encodeBMP(img, path) : encodePNGInfo(img, path, info);
+}
+void rendererInfo(const struct renderer *r, struct renderInfo *out) {            /* c-ray.c:88-95 fills struct renderInfo the same way */
+	memset(out, 0, sizeof *out);
+	if (!r) return;
+	out->samples = r->prefs.sampleCount; out->bounces = r->prefs.bounces;
+	out->threadCount = r->world > 1 ? r->world : r->prefs.threadCount;
+	out->renderSeconds = r->state.renderSeconds;
 }

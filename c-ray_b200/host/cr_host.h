@@ -155,3 +155,8 @@ void *gpuRenderThread(void *arg);
 int writeImage(const struct texture8 *img, const char *path, enum fileType type);
 int encodeBMP(const struct texture8 *img, const char *path);
 int encodePNG(const struct texture8 *img, const char *path);
+/* what the reference stores in the PNG's tEXt chunks (struct renderInfo, src/datatypes/image/imagefile.h:13-21; png.c:29-56) */
+struct renderInfo { int samples, bounces, threadCount; double renderSeconds; };
+int encodePNGInfo(const struct texture8 *img, const char *path, const struct renderInfo *info);
+int writeImageInfo(const struct texture8 *img, const char *path, enum fileType type, const struct renderInfo *info);
+void rendererInfo(const struct renderer *r, struct renderInfo *out);

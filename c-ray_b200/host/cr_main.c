@@ -44,7 +44,9 @@ int main(int argc, char **argv) {
 	if (out) {
 		const size_t n = strlen(out);
 		const enum fileType ft = (n > 4 && !strcmp(out + n - 4, ".bmp")) ? bmp : png;
-		if (writeImage(img, out, ft) != 0) { fprintf(stderr, "cannot write %s\n", out); rc = 4; }
+		struct renderInfo info;
+		rendererInfo(r, &info);
+		if (writeImageInfo(img, out, ft, &info) != 0) { fprintf(stderr, "cannot write %s\n", out); rc = 4; }
 		else if (!quiet) printf("Saved result to %s\n", out);
 	}
 	if (dump) {

@@ -123,6 +123,35 @@ def test_encoders_roundtrip(host, tmp_path):
     assert np.array_equal(px[::-1, :, ::-1], img)       # bottom-up, BGR (bmp.c:19-71)
 
 
+def test_png_carries_the_reference_text_labels(host, tmp_path):
+    """png.c:29-56: the reference labels its PNGs with uncompressed tEXt chunks (version, source, samples, bounces, render time,
+    threads, uname); same keywords here, placed before the image data, and our own decoder still reads the file."""
+    class Info(C.Structure):
+        _fields_ = [("samples", C.c_int), ("bounces", C.c_int), ("threadCount", C.c_int), ("renderSeconds", C.c_double)]
+    img = np.arange(5 * 7 * 3, dtype=np.uint8).reshape(5, 7, 3)
+    t = Texture8(7, 5, img.ctypes.data_as(C.POINTER(C.c_uint8)))
+    info = Info(1000, 32, 8, 83.4)
+    p = str(tmp_path / "t.png")
+    host.writeImageInfo.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+    assert host.writeImageInfo(C.byref(t), p.encode(), 1, C.byref(info)) == 0
+    b = open(p, "rb").read()
+    texts, pos, order = {}, 8, []
+    while pos < len(b):
+        n, tag = struct.unpack(">I4s", b[pos:pos + 8])
+        data = b[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", b[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + data) & 0xFFFFFFFF
+        order.append(tag)
+        if tag == b"tEXt":
+            k, v = data.split(b"\0", 1)
+            texts[k.decode()] = v.decode()
+        pos += 12 + n
+    assert [k for k in texts] == ["C-ray Version", "C-ray Source", "C-ray Samples", "C-ray Bounces", "C-ray RenderTime", "C-ray Threads", "C-ray SysInfo"]
+    assert (texts["C-ray Samples"], texts["C-ray Bounces"], texts["C-ray Threads"], texts["C-ray RenderTime"]) == ("1000", "32", "8", "1m 23s")
+    assert texts["C-ray Source"] == "https://github.com/vkoskiv/c-ray"
+    assert order[0] == b"IHDR" and order.index(b"IDAT") > max(i for i, t_ in enumerate(order) if t_ == b"tEXt") and order[-1] == b"IEND"
+    assert np.array_equal(decode_png(p), img)
+
+
 def test_png_encoder_multi_band_stream(host, tmp_path):
     """Images above ~1 MB of scanlines are deflated in parallel bands (one IDAT each); the concatenation must be ONE valid
     zlib stream (header, byte-aligned blocks, combined Adler-32) that any decoder accepts."""
