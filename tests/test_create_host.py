@@ -58,8 +58,11 @@ def test_big_scene_threaded_repack_is_deterministic(harness):
     assert a[0] > 274245 * 48 + 274245 * 80 + 114552 * 64 + 20 * 2 ** 20
 
 
-def test_malformed_scenes_are_rejected_not_crashing(harness, tmp_path):
-    src = open(os.path.join(GOLDEN, "g_legacy.crscene"), "rb").read()
+@pytest.mark.parametrize("name", ["g_legacy", "g_f4"])
+def test_malformed_scenes_are_rejected_not_crashing(harness, tmp_path, name):
+    """random byte damage in the array sections (indices, counts, node kinds and operand indices — g_f4 carries the math / vecmath /
+    fresnel / combine graphs of the complete interpreter): crgpu_prepare must answer with an error code or accept, never crash"""
+    src = open(os.path.join(GOLDEN, name + ".crscene"), "rb").read()
     rng = random.Random(3)
     rejected = 0
     for i in range(150):
