@@ -5,8 +5,8 @@
  * prefs.threadCount workers through the thread-function slot, poll their renderThreadState every 16 ms
  * (progress line ~4x/s: percentage of tiles, μs/path, ETA, Msamples/s — renderer.c:126-158), join, return the
  * image.  The workers are gpuRenderThread (one per CUDA device) instead of renderThread (renderer.c:258-327):
- * same tile queue (nextTile), same published fields, same pause flag, but a tile's passes are handed to
- * crgpu_render_tiles in one call and pixels never touch the CPU.
+ * same tile array, same published fields, same pause flag, but a worker takes its whole share of the tiles at once (a spatial
+ * interleave, see gpuRenderThread) and hands it to crgpu_render_tiles as ONE wavefront; pixels never touch the CPU.
  *
  * Per frame a worker uploads the prepared scene (one pinned host->device copy, in parallel on all GPUs), renders,
  * and releases its replica into libcrgpu's per-device cache.  With more than one GPU the tiles are gathered on
@@ -199,18 +199,6 @@ int joinRanks(struct renderer *r, const void *id128, int rank, int world, int de
 	return 0;
 }
 
-/* How many tiles a GPU worker takes from the queue per trip.  A CPU thread takes one (renderer.c:265,318); a GPU
- * wavefront pays a fixed ~7 ms latency chain per batch, so a worker takes enough tiles to put ~64M paths in flight,
- * but never more than its fair share of what is left (keeps several GPUs balanced). */
-static int tiles_per_trip(const struct renderer *r) {
-	const double tilePaths = (double)r->prefs.tileWidth * r->prefs.tileHeight * (double)r->prefs.sampleCount;
-	int want = (int)(64.0 * 1048576.0 / (tilePaths > 1.0 ? tilePaths : 1.0)) + 1;
-	const int left = r->state.tileCount - r->state.finishedTileCount;
-	const int share = (left + r->prefs.threadCount - 1) / (r->prefs.threadCount > 0 ? r->prefs.threadCount : 1);
-	if (want > share) want = share;
-	return want < 1 ? 1 : want;
-}
-
 /* One-process-per-GPU jobs: drain the tile queue, keep the tiles of this rank.  Static placement (deterministic, so every
  * rank knows every tile's owner for the gather without talking), interleaved IN SPACE: tile (tx, ty) of the tile grid belongs to
  * rank (tx + 5 ty) % world.  Dealing by queue position (k % world) looks equivalent but is not: the default "fromMiddle" order
@@ -261,14 +249,22 @@ void *gpuRenderThread(void *arg) {
 		if (ranked) {
 			got = takeRankTiles(r, rects, nums);
 		} else {
-			/* take a handful of tiles from the shared queue (nextTile, tile.c:22-45) */
-			const int want = tiles_per_trip(r);
-			while (got < want) {
-				struct renderTile tile = nextTile(r);
-				if (tile.tileNum == -1) break;
-				rects[4 * got] = tile.begin.x; rects[4 * got + 1] = tile.begin.y; rects[4 * got + 2] = tile.end.x; rects[4 * got + 3] = tile.end.y;
-				nums[got++] = tile.tileNum;
+			/* In-process workers share the reference's tile array but not its one-tile-at-a-time queue (nextTile, tile.c:22-45): a GPU
+			 * wants its whole share as ONE wavefront (every trip pays the ~7 ms bounce chain and a tail nothing overlaps), and a share
+			 * made of consecutive queue positions is a spatial cluster ("fromMiddle": the centre, where the statue is).  So worker t
+			 * takes, once, the tiles the spatial interleave gives it — the same placement as ranks (tile_rank).  Measured on 8 B200
+			 * with trips of 17 queue-consecutive tiles: 0.312 s per C2 frame against 0.164 s for 8 ranks (profiles/r02_cli_hdr_j8.txt). */
+			const int workers = r->prefs.threadCount > 0 ? r->prefs.threadCount : 1;
+			for (int i = 0; i < r->state.tileCount; ++i) {
+				struct renderTile *t = &r->state.renderTiles[i];
+				if (tile_rank(r, t, workers) != ts->thread_num) continue;
+				rects[4 * got] = t->begin.x; rects[4 * got + 1] = t->begin.y; rects[4 * got + 2] = t->end.x; rects[4 * got + 3] = t->end.y;
+				nums[got++] = i;
+				t->isRendering = true;
 			}
+			pthread_mutex_lock(&r->state.tileMutex);
+			r->state.finishedTileCount += got;                                     /* what the progress line reads */
+			pthread_mutex_unlock(&r->state.tileMutex);
 		}
 		if (got == 0) break;
 		ts->currentTileNum = nums[0];
@@ -291,7 +287,7 @@ void *gpuRenderThread(void *arg) {
 			if (!ranked) r->state.tileOwner[nums[i]] = ts->thread_num;
 		}
 		ts->currentTileNum = -1;
-		if (ranked) break;                                                        /* the rank's whole share was one trip */
+		break;                                                                    /* the worker's whole share was one trip */
 	}
 	free(rects); free(nums);
 	pthread_mutex_lock(&r->state.doneMutex);
